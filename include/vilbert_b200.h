@@ -1,0 +1,155 @@
+/* vilbert_b200 -- C ABI of the B200-native ViLBERT multi-task forward.
+ *
+ * The reference has no FFI for this path: its boundary is the Python object protocol that
+ * /root/reference/worker.py fixes:
+ *     config = BertConfig.from_json_file(...)                          worker.py:495, 506-522
+ *     model  = VILBertForVLTasks.from_pretrained(ckpt, config=config,
+ *                                                num_labels=3129, ...) worker.py:530-532
+ *     model.eval(); model.cuda(0)                                      worker.py:534-536
+ *     out10  = model(question, features, spatials, segment_ids, input_mask, image_mask,
+ *                    co_attention_mask, task_tokens, output_all_attention_masks=True)
+ *                                                                      worker.py:286-289
+ * The entry points below are exactly what a binding for that protocol needs, and nothing else:
+ * vb200_create <- from_pretrained + cuda(i); vb200_forward <- __call__; vb200_destroy <- del.
+ * The Python shim in vilbert-multi-task_b200/ (ctypes) implements the protocol on top of them; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success or a
+ * negative vb200_status; no exception crosses the boundary; vb200_last_error() returns the message of the
+ * last failure on that handle (or of the last failed vb200_create when handle == NULL).
+ * vb200_forward is asynchronous on the caller's stream (no hidden synchronisation); input and output
+ * buffers are owned by the caller; one handle serves one stream at a time (workspaces are per handle).
+ */
+#ifndef VILBERT_B200_H
+#define VILBERT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_ABI_VERSION 1
+
+typedef struct vb200_engine* vb200_handle;
+
+typedef enum {
+    VB200_OK = 0,
+    VB200_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+    VB200_ERR_CONFIG = -2,       /* config JSON could not be parsed or is unsupported */
+    VB200_ERR_CHECKPOINT = -3,   /* missing / unexpected / mis-shaped state_dict entry */
+    VB200_ERR_CUDA = -4,         /* CUDA runtime or driver error (message has the detail) */
+    VB200_ERR_NO_DEVICE = -5     /* no sm_100 device: there is deliberately no CPU fallback */
+} vb200_status;
+
+typedef enum { VB200_F32 = 0, VB200_F16 = 1, VB200_BF16 = 2 } vb200_dtype;
+
+/* One entry of the flat checkpoint state_dict (worker.py:470, 530-532): upstream key name, host pointer. */
+typedef struct {
+    const char* name;        /* e.g. "bert.encoder.c_layer.3.biattention.query1.weight" ("module." prefix accepted) */
+    int32_t dtype;           /* vb200_dtype */
+    int32_t ndim;            /* 1 or 2 */
+    int64_t shape[2];        /* nn.Linear weights are [out, in] row-major */
+    const void* data;        /* host memory, contiguous */
+} vb200_tensor;
+
+/* Which elements of the reference's 10-tuple (worker.py:287) to compute. */
+enum {
+    VB200_OUT_VIL_PREDICTION = 1 << 0,         /* [B, num_labels]  VQA / VG-QA            worker.py:296 */
+    VB200_OUT_VIL_PREDICTION_GQA = 1 << 1,     /* [B, 1533]        GQA                    worker.py:313 */
+    VB200_OUT_VIL_LOGIT = 1 << 2,              /* [B, 1]           retrieval              worker.py:359 */
+    VB200_OUT_VIL_BINARY_PREDICTION = 1 << 3,  /* [B/2, 2] (B even) / [B, 2] (B odd)  NLVR2  worker.py:329 */
+    VB200_OUT_VIL_TRI_PREDICTION = 1 << 4,     /* [B, 3]           SNLI-VE                worker.py:345 */
+    VB200_OUT_VISION_PREDICTION = 1 << 5,      /* [B, V, v_target_size]  pre-training head, unused by the worker */
+    VB200_OUT_VISION_LOGIT = 1 << 6,           /* [B, V, 1]        grounding              worker.py:374 */
+    VB200_OUT_LINGUISIC_PREDICTION = 1 << 7,   /* [B, T, vocab]    pre-training head, unused by the worker */
+    VB200_OUT_LINGUISIC_LOGIT = 1 << 8,        /* [B, T, 1]        never read by the worker */
+    VB200_OUT_TASK_HEADS = 0x15F,              /* the seven task heads (everything but the two pre-training heads) */
+    VB200_OUT_ALL = 0x1FF
+};
+
+/* Inputs of one forward, in the dtypes the worker builds them (worker.py:416-419, 452-455).
+ * T = Tin + 1 when config.task_specific_tokens (worker.py:516-517).  co_attention_mask is accepted for
+ * signature compatibility and ignored, as upstream ignores it (worker passes zeros, worker.py:455). */
+typedef struct {
+    int32_t batch;                 /* B  */
+    int32_t n_tokens;              /* Tin */
+    int32_t n_regions;             /* V  */
+    const int64_t* question;       /* [B, Tin] token ids */
+    const float* features;         /* [B, V, v_feature_size] */
+    const float* spatials;         /* [B, V, 5] */
+    const int64_t* segment_ids;    /* [B, Tin] */
+    const int64_t* input_mask;     /* [B, Tin] */
+    const uint8_t* image_mask;     /* [B, V] */
+    const float* co_attention_mask;/* [B, V, Tin] or NULL; ignored */
+    const int64_t* task_tokens;    /* [B, 1] */
+} vb200_inputs;
+
+/* Caller-allocated fp32 outputs; a NULL pointer (or a cleared select bit) skips that output. */
+typedef struct {
+    float* vil_prediction;         /* [B, num_labels] */
+    float* vil_prediction_gqa;     /* [B, gqa_labels] */
+    float* vil_logit;              /* [B, 1] */
+    float* vil_binary_prediction;  /* [B/2, 2] if B even else [B, 2] */
+    float* vil_tri_prediction;     /* [B, 3] */
+    float* vision_prediction;      /* [B, V, v_target_size] */
+    float* vision_logit;           /* [B, V, 1] */
+    float* linguisic_prediction;   /* [B, T, vocab] */
+    float* linguisic_logit;        /* [B, T, 1] */
+    float* sequence_output_t;      /* optional debug tap: final text stream  [B, T, hidden]   (fp32) */
+    float* sequence_output_v;      /* optional debug tap: final image stream [B, V, v_hidden] (fp32) */
+    float* pooled_output;          /* optional debug tap: pooled_t * pooled_v [B, bi_hidden] */
+} vb200_outputs;
+
+/* Engine options (all optional; zero-initialise for defaults).  Flags are tri-state: 0 default, 1 on, -1 off. */
+typedef struct {
+    int32_t device;                /* CUDA ordinal */
+    int32_t num_labels;            /* vil_prediction width; 0 -> taken from the checkpoint (worker.py:523: 3129) */
+    int32_t use_cuda_graph;        /* default on: each (B,Tin,V,select) plan is captured once and replayed */
+    int32_t use_pdl;               /* default off: programmatic dependent launch between consecutive kernels */
+    int32_t strict;                /* default on: unexpected checkpoint keys are an error */
+} vb200_options;
+
+int vb200_abi_version(void);
+
+/* from_pretrained + cuda(device): parse the BertConfig JSON, audit the state_dict against the upstream key list,
+ * repack weights to device (bf16 GEMM operands, fp32 LayerNorm/bias/embedding tables). */
+int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor* tensors, const vb200_options* opt,
+                 vb200_handle* out);
+int vb200_destroy(vb200_handle h);
+const char* vb200_last_error(vb200_handle h);
+
+/* Device-pointer forward (what worker.py:286-289 does): all vb200_inputs / vb200_outputs pointers are device
+ * memory on the engine's device; enqueued on `cuda_stream` (a cudaStream_t passed as void*). */
+int vb200_forward(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, void* cuda_stream);
+
+/* Host-pointer forward: same, but every pointer is HOST memory (pinned for full speed); copies in, runs, copies
+ * the selected outputs back and synchronises the stream before returning. */
+int vb200_forward_host(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select,
+                       void* cuda_stream);
+
+/* Introspection used by the tests / bench: number of kernels one forward of this shape launches,
+ * algorithmic FLOPs of it, model dimensions. */
+int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select,
+                    int64_t* n_launches, double* flops);
+int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
+
+/* ---- Kernel-level entry points (device pointers), used by the parity tests and the roofline bench.  ---- */
+/* y = epilogue(x[M,K] (bf16) . w[N,K]^T (bf16)); act: 0 none, 1 GELU(erf), 2 ReLU; LayerNorm applied when gamma != NULL. */
+int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t ld_w, const float* bias,
+                 const float* residual, int64_t ld_res, const float* gamma, const float* beta, float eps, int32_t act,
+                 void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
+                 int32_t block_n, int32_t use_pdl, void* cuda_stream);
+/* ctx = softmax(Q K^T / sqrt(d) + mask) V, qkv rows = [Q | K | V] (bf16), mask_add fp32 [B, L]. */
+int vb200_self_attention(const void* qkv_bf16, int64_t ld_qkv, int32_t hidden, const float* mask_add, void* ctx_bf16,
+                         int64_t ld_ctx, int32_t B, int32_t L, int32_t heads, int32_t head_dim, void* cuda_stream);
+int vb200_co_attention(const void* qkv_img_bf16, int64_t ld_img, const void* qkv_txt_bf16, int64_t ld_txt,
+                       int32_t hidden, const float* img_mask_add, const float* txt_mask_add, void* ctx_txt_bf16,
+                       int64_t ld_ctx_txt, void* ctx_img_bf16, int64_t ld_ctx_img, int32_t B, int32_t T, int32_t V,
+                       int32_t heads, int32_t head_dim, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILBERT_B200_H */

@@ -1,0 +1,273 @@
+"""VILBertForVLTasks: the object protocol of the reference worker on top of the C ABI.
+
+    config = BertConfig.from_json_file(path)                                   worker.py:495, 506
+    model  = VILBertForVLTasks.from_pretrained(ckpt, config=config,
+                                               num_labels=3129, default_gpu=True)   worker.py:530-532
+    model.eval(); model.cuda(0)                                                worker.py:534-536
+    out10  = model(question, features, spatials, segment_ids, input_mask, image_mask,
+                   co_attention_mask, task_tokens, output_all_attention_masks=True)  worker.py:286-289
+
+Everything between the input tensors and the ten outputs runs in libvilbert_b200.so (hand-written sm_100a
+kernels).  torch is used only as the tensor container and for the CUDA stream.  No CPU path exists: calling
+the model without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .config import BertConfig
+
+_DTYPES = {torch.float32: L.F32, torch.float16: L.F16, torch.bfloat16: L.BF16}
+
+
+def _normalise_state_dict(sd) -> Dict[str, torch.Tensor]:
+    if isinstance(sd, dict) and "state_dict" in sd and isinstance(sd["state_dict"], dict):
+        sd = sd["state_dict"]
+    if isinstance(sd, dict) and "model_state_dict" in sd and isinstance(sd["model_state_dict"], dict):
+        sd = sd["model_state_dict"]
+    out = {}
+    for k, v in sd.items():
+        if not torch.is_tensor(v):
+            continue
+        if v.dtype in (torch.int64, torch.int32, torch.bool) or v.dim() == 0 or v.dim() > 2:
+            continue                      # e.g. position_ids buffers, num_batches_tracked
+        if v.dtype not in _DTYPES:
+            v = v.float()
+        out[k] = v.detach().cpu().contiguous()
+    return out
+
+
+class VILBertForVLTasks(object):
+    """Drop-in for ``vilbert.vilbert.VILBertForVLTasks`` on the inference path the worker uses."""
+
+    def __init__(self, config: BertConfig, num_labels: int = 3129, state_dict=None, default_gpu: bool = True,
+                 use_cuda_graph: bool = True, use_pdl: bool = False, strict: bool = True):
+        self.config = config
+        self.num_labels = num_labels
+        self._sd = _normalise_state_dict(state_dict) if state_dict is not None else None
+        self._handle = None
+        self._device = None
+        self._opts = dict(use_cuda_graph=use_cuda_graph, use_pdl=use_pdl, strict=strict)
+        self.training = False
+        self._dims = {}
+
+    # ------------------------------------------------------------------ reference construction protocol
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, config=None, num_labels=3129, default_gpu=True,
+                        state_dict=None, **kwargs):
+        if config is None:
+            raise ValueError("config is required (worker.py:530-532 always passes it)")
+        if state_dict is None:
+            if isinstance(pretrained_model_name_or_path, dict):
+                state_dict = pretrained_model_name_or_path
+            else:
+                state_dict = torch.load(pretrained_model_name_or_path, map_location="cpu")
+        return cls(config, num_labels=num_labels, state_dict=state_dict, default_gpu=default_gpu, **kwargs)
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise L.VilbertB200Error("vilbert_b200 is an inference engine; train() is not supported")
+        return self
+
+    def cuda(self, device=0):
+        if isinstance(device, torch.device):
+            device = device.index or 0
+        device = 0 if device is None else int(device)
+        if self._handle is not None and self._device == device:
+            return self
+        self._create(device)
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.VilbertB200Error("vilbert_b200 runs on sm_100 GPUs only; there is no CPU path")
+        return self.cuda(device.index or 0)
+
+    def half(self):            # operands are bf16 already; accepted for call-site compatibility
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def state_dict(self):
+        return dict(self._sd) if self._sd is not None else {}
+
+    # ------------------------------------------------------------------ engine lifetime
+    def _config_json(self) -> bytes:
+        d = {k: v for k, v in self.config.to_dict().items()
+             if isinstance(v, (int, float, str, bool, list)) or v is None}
+        return json.dumps(d).encode()
+
+    def _create(self, device: int):
+        lib = L.load()
+        if self._sd is None:
+            raise L.VilbertB200Error("no state_dict: build the model with from_pretrained(...)")
+        if not torch.cuda.is_available():
+            raise L.VilbertB200Error("no CUDA device visible; vilbert_b200 has no CPU fallback")
+        self.close()
+        names = [k.encode() for k in self._sd]
+        arr = (L.Tensor * len(self._sd))()
+        keep = []
+        for i, (k, v) in enumerate(self._sd.items()):
+            t = arr[i]
+            t.name = names[i]
+            t.dtype = _DTYPES[v.dtype]
+            t.ndim = v.dim()
+            t.shape[0] = v.shape[0]
+            t.shape[1] = v.shape[1] if v.dim() == 2 else 0
+            t.data = v.data_ptr()
+            keep.append(v)
+        opt = L.Options()
+        opt.device = device
+        opt.num_labels = int(self.num_labels or 0)
+        opt.use_cuda_graph = 1 if self._opts["use_cuda_graph"] else -1
+        opt.use_pdl = 1 if self._opts["use_pdl"] else 0
+        opt.strict = 1 if self._opts["strict"] else -1
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = lib.vb200_create(self._config_json(), len(self._sd), arr, C.byref(opt), C.byref(h))
+        L.check(rc, None)
+        self._handle, self._device = h, device
+        for key in ("hidden_size", "v_hidden_size", "bi_hidden_size", "vocab_size", "v_target_size",
+                    "v_feature_size", "num_labels", "gqa_labels", "task_specific_tokens", "weight_bytes"):
+            v = C.c_int64()
+            L.check(lib.vb200_model_dim(h, key.encode(), C.byref(v)), h)
+            self._dims[key] = v.value
+
+    def close(self):
+        if self._handle is not None:
+            L.load().vb200_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward
+    def _out_shapes(self, B, T, V, select):
+        d = self._dims
+        shapes = {
+            "vil_prediction": (L.OUT_VIL_PREDICTION, (B, d["num_labels"])),
+            "vil_prediction_gqa": (L.OUT_VIL_PREDICTION_GQA, (B, d["gqa_labels"])),
+            "vil_logit": (L.OUT_VIL_LOGIT, (B, 1)),
+            "vil_binary_prediction": (L.OUT_VIL_BINARY_PREDICTION, (B // 2, 2) if B % 2 == 0 else (B, 2)),
+            "vil_tri_prediction": (L.OUT_VIL_TRI_PREDICTION, (B, 3)),
+            "vision_prediction": (L.OUT_VISION_PREDICTION, (B, V, d["v_target_size"])),
+            "vision_logit": (L.OUT_VISION_LOGIT, (B, V, 1)),
+            "linguisic_prediction": (L.OUT_LINGUISIC_PREDICTION, (B, T, d["vocab_size"])),
+            "linguisic_logit": (L.OUT_LINGUISIC_LOGIT, (B, T, 1)),
+        }
+        return {k: s for k, (bit, s) in shapes.items() if select & bit}
+
+    def plan_info(self, batch, n_tokens, n_regions, select=L.OUT_TASK_HEADS):
+        n, f = C.c_int64(), C.c_double()
+        L.check(L.load().vb200_plan_info(self._handle, batch, n_tokens, n_regions, select, C.byref(n), C.byref(f)),
+                self._handle)
+        return n.value, f.value
+
+    def _prep(self, question, features, spatials, segment_ids, input_mask, image_mask, task_tokens, device):
+        def dev(t, dtype):
+            if not torch.is_tensor(t):
+                t = torch.as_tensor(t)
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            if t.device != device:
+                t = t.to(device, non_blocking=True)
+            return t.contiguous()
+        B, Tin = question.shape
+        V = features.shape[1]
+        q = dev(question, torch.int64)
+        f = dev(features, torch.float32)
+        s = dev(spatials, torch.float32)
+        seg = dev(segment_ids if segment_ids is not None else torch.zeros_like(question), torch.int64)
+        im = dev(input_mask if input_mask is not None else torch.ones_like(question), torch.int64)
+        vm = dev(image_mask if image_mask is not None else torch.ones(B, V, dtype=torch.uint8), torch.uint8)
+        if task_tokens is None:
+            task_tokens = torch.zeros(B, 1, dtype=torch.int64)
+        tk = dev(task_tokens, torch.int64).reshape(B, -1)[:, :1].contiguous()
+        if tuple(f.shape) != (B, V, self._dims["v_feature_size"]) or tuple(s.shape) != (B, V, 5) \
+                or tuple(seg.shape) != (B, Tin) or tuple(im.shape) != (B, Tin) or tuple(vm.shape) != (B, V):
+            raise ValueError("input shapes do not match the worker.py:416-455 layout")
+        return q, f, s, seg, im, vm, tk
+
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
+
+    @torch.no_grad()
+    def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None,
+                image_attention_mask=None, co_attention_mask=None, task_ids=None,
+                output_all_encoded_layers=False, output_all_attention_masks=False,
+                compute_pretraining_heads=False, select: Optional[int] = None, debug_taps: bool = False):
+        """Positional signature and 10-tuple of worker.py:286-289.
+
+        ``vision_prediction`` / ``linguisic_prediction`` (the pre-training heads, elements 5 and 7, never read
+        by the worker) are computed only with ``compute_pretraining_heads=True`` and are ``None`` otherwise;
+        ``attn_data_list`` (element 9, never read by the worker) is returned empty.
+        """
+        if self._handle is None:
+            if torch.is_tensor(input_txt) and input_txt.is_cuda:
+                self.cuda(input_txt.device.index)
+            else:
+                raise L.VilbertB200Error("call model.cuda(i) first (worker.py:536); there is no CPU path")
+        lib = L.load()
+        device = torch.device("cuda", self._device)
+        if select is None:
+            select = L.OUT_ALL if compute_pretraining_heads else L.OUT_TASK_HEADS
+        q, f, s, seg, im, vm, tk = self._prep(input_txt, input_imgs, image_loc, token_type_ids, attention_mask,
+                                              image_attention_mask, task_ids, device)
+        B, Tin = q.shape
+        V = f.shape[1]
+        T = Tin + (1 if self._dims["task_specific_tokens"] else 0)
+        inp = L.Inputs(B, Tin, V, q.data_ptr(), f.data_ptr(), s.data_ptr(), seg.data_ptr(), im.data_ptr(),
+                       vm.data_ptr(), None, tk.data_ptr())
+        outs = {k: torch.empty(shape, dtype=torch.float32, device=device)
+                for k, shape in self._out_shapes(B, T, V, select).items()}
+        if debug_taps:
+            outs["sequence_output_t"] = torch.empty(B, T, self._dims["hidden_size"], dtype=torch.float32, device=device)
+            outs["sequence_output_v"] = torch.empty(B, V, self._dims["v_hidden_size"], dtype=torch.float32, device=device)
+            outs["pooled_output"] = torch.empty(B, self._dims["bi_hidden_size"], dtype=torch.float32, device=device)
+        o = L.Outputs()
+        for k, t in outs.items():
+            setattr(o, k, t.data_ptr())
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            L.check(lib.vb200_forward(self._handle, C.byref(inp), C.byref(o), select, C.c_void_p(stream)), self._handle)
+        g = outs.get
+        result = (g("vil_prediction"), g("vil_prediction_gqa"), g("vil_logit"), g("vil_binary_prediction"),
+                  g("vil_tri_prediction"), g("vision_prediction"), g("vision_logit"), g("linguisic_prediction"),
+                  g("linguisic_logit"), [])
+        if debug_taps:
+            return result, {k: outs[k] for k in ("sequence_output_t", "sequence_output_v", "pooled_output")}
+        return result
+
+    # ------------------------------------------------------------------ host-buffer entry (bench e2e, serving)
+    def forward_host(self, question, features, spatials, segment_ids, input_mask, image_mask, task_tokens,
+                     out: Dict[str, torch.Tensor], select: int = L.OUT_VIL_PREDICTION):
+        """vb200_forward_host: HOST (ideally pinned) tensors in, HOST tensors out; H2D + forward + D2H + sync."""
+        lib = L.load()
+        B, Tin = question.shape
+        V = features.shape[1]
+        inp = L.Inputs(B, Tin, V, question.data_ptr(), features.data_ptr(), spatials.data_ptr(),
+                       segment_ids.data_ptr(), input_mask.data_ptr(), image_mask.data_ptr(), None,
+                       task_tokens.data_ptr())
+        o = L.Outputs()
+        for k, t in out.items():
+            setattr(o, k, t.data_ptr())
+        device = torch.device("cuda", self._device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            L.check(lib.vb200_forward_host(self._handle, C.byref(inp), C.byref(o), select, C.c_void_p(stream)),
+                    self._handle)
+        return out

@@ -1,0 +1,12 @@
+"""Import alias: ``import vilbert_b200`` loads the package in ``vilbert-multi-task_b200/``
+(a directory name with hyphens cannot be imported directly)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vilbert-multi-task_b200")
+_spec = importlib.util.spec_from_file_location("vilbert_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["vilbert_b200"] = _mod
+_spec.loader.exec_module(_mod)
