@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- image-text pairs/sec through the ViLBERT VQA head (36 regions x 30 tokens), BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU PyTorch path (oracle port)
+
+A "step" is one forward of one batch of `--batch` pairs (default 64 = BASELINE.json configs[1]) per GPU;
+batches shard over ranks with no collective -> weak scaling.  Rank 0 prints ONE JSON line.
+
+value      : whole-job pairs/s with inputs resident in HBM (device-pointer C-ABI call, CUDA-event timed, max over ranks)
+e2e        : the same through the host-buffer C-ABI call (pinned host inputs -> H2D -> forward -> D2H logits)
+roofline   : tensor-pipe roofline of the dominant kernel family (the tcgen05 GEMMs, 97 % of the FLOPs)
+cpu_baseline: the fp32 PyTorch oracle (port of the reference's eager forward, all heads as the reference runs
+             them) timed on this box's host cores, rank 0 at N=1 only, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-text pairs/sec (VQA head, 36 regions x 30 tok)"
+UNIT = "pairs/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
+    p.add_argument("--n-tokens", type=int, default=30)
+    p.add_argument("--n-regions", type=int, default=36)
+    p.add_argument("--rotate", type=int, default=8, help="distinct resident input batches cycled through (L2 defeat)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--pdl", action="store_true")
+    p.add_argument("--all-heads", action="store_true", help="compute the seven task heads instead of VQA only")
+    return p.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm": d["hbm_gbs"], "src": "measured"}
+    except Exception:
+        return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz, self.err = index, False, [], set(), None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake": 0x80, "sw_power_cap": 0x4, "sync_boost": 0x10}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:          # NVML missing: report it, never fail the bench
+            self.err = repr(e)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "error": self.err}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_model(sd, cfg_dict, num_labels):
+    """The ONLY place bench.py touches oracle/: the CPU baseline legs."""
+    import torch
+    from oracle import vilbert_ref as R
+    m = R.VILBertForVLTasks(R.RefConfig(**{k: v for k, v in cfg_dict.items() if k in R.DEFAULT_CONFIG}), num_labels=num_labels)
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def time_oracle(model, req, steps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model(*req, output_all_attention_masks=True, compute_pretraining_heads=True)   # as the reference runs it
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    import torch
+    import vilbert_b200 as vb
+    from vilbert_b200 import synthetic as S
+    cfg = vb.BertConfig(task_specific_tokens=True, visualization=True)
+    sd = S.synthetic_state_dict(cfg, seed=42)
+    model = oracle_model(sd, cfg.to_dict(), 3129)
+    # bounded sample: ~2400 pairs in total (about two minutes of host work), never more than the real batch
+    ref_batch = max(4, min(args.batch, 2400 // max(1, args.steps)))
+    req = S.synthetic_request(ref_batch, args.n_tokens, args.n_regions, seed=1234)
+    steps = args.steps
+    times = time_oracle(model, req, steps, max(1, min(args.warmup, 2)))
+    total = sum(times)
+    value = ref_batch * len(times) / total
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch={args.batch} VQA forward, {args.n_regions} regions x {args.n_tokens} tokens "
+                                   "(BASELINE.json configs[1]); reference arm = fp32 PyTorch oracle port on host cores, "
+                                   "all heads + pre-training heads as the reference executes them",
+                       "global_batch": args.batch, "parallelism": "cpu"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{len(times)} forwards of {ref_batch} pairs each (bounded sample of the batch-{args.batch} "
+                                       f"workload; torch fp32, {torch.get_num_threads()} threads)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import vilbert_b200 as vb
+    from vilbert_b200 import synthetic as S
+    from vilbert_b200 import _lib as L
+
+    rank, local_rank, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the vilbert_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, Tin, V = args.batch, args.n_tokens, args.n_regions
+    cfg = vb.BertConfig(task_specific_tokens=True, visualization=True)       # worker.py:509-522
+    sd = S.synthetic_state_dict(cfg, seed=42)
+    model = vb.VILBertForVLTasks.from_pretrained(sd, config=cfg, num_labels=3129, use_cuda_graph=not args.no_graph,
+                                                 use_pdl=args.pdl).eval().cuda(local_rank)
+    select = L.OUT_TASK_HEADS if args.all_heads else L.OUT_VIL_PREDICTION
+    n_launch, flops = model.plan_info(B, Tin, V, select)
+
+    # resident inputs: `rotate` distinct batches (8 x 19 MB > 126 MB L2 together with 466 MB of weights)
+    reqs = [S.synthetic_request(B, Tin, V, seed=1234 + rank * 1000 + i) for i in range(args.rotate)]
+    dreqs = [[t.to(dev) for t in r] for r in reqs]
+    in_bytes = sum(t.numel() * t.element_size() for i, t in enumerate(reqs[0]) if i != 6)
+
+    def step(i):
+        return model(*dreqs[i % args.rotate], select=select)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        out = step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+    e1.record()
+    sync_all()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.join(timeout=1.0)
+    assert torch.isfinite(out[0]).all(), "non-finite logits"
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host-buffer C-ABI call, pinned inputs, H2D + forward + D2H of the logits inside the timed region
+    hreqs = [[t.pin_memory() for i, t in enumerate(r) if i != 6] for r in reqs]
+    hout = {"vil_prediction": torch.empty(B, 3129, dtype=torch.float32).pin_memory()}
+    out_bytes = hout["vil_prediction"].numel() * 4
+
+    def estep(i):
+        q, f, s, seg, im, vm, tk = hreqs[i % args.rotate]
+        model.forward_host(q, f, s, seg, im, vm, tk, hout, select=L.OUT_VIL_PREDICTION)
+
+    for i in range(max(args.warmup, 3)):
+        estep(i)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        estep(i)                       # synchronises its stream before returning
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = B * world * args.steps / e2e_s
+    # sanity: host path and device path agree
+    chk = model(*dreqs[(args.steps - 1) % args.rotate], select=L.OUT_VIL_PREDICTION)[0].cpu()
+    assert torch.allclose(chk, hout["vil_prediction"], atol=1e-5), "host/device C-ABI paths disagree"
+
+    pk = peaks()
+    tflops = flops * args.steps / (ms * 1e-3) / 1e12           # per GPU (ms is the max over ranks)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"batch={B} per GPU, VQA head, {V} regions x {Tin} tokens (BASELINE.json configs[1]), "
+                                   f"bf16 operands / fp32 accumulate; random-init 268M-param ViLBERT (seed 42)",
+                       "global_batch": B * world, "per_gpu_batch": B, "n_tokens": Tin, "n_regions": V,
+                       "parallelism": f"dp{world} (batch sharding, no collective)",
+                       "l2": f"inputs rotate over {args.rotate} resident batches ({args.rotate * in_bytes / 1e6:.0f} MB) "
+                             f"+ {model._dims['weight_bytes'] / 1e6:.0f} MB of weights > 126 MB L2",
+                       "cuda_graph": not args.no_graph, "pdl": bool(args.pdl),
+                       "heads": "task heads" if args.all_heads else "vil_prediction"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(n_launch) * args.steps,
+            "launches_per_step": int(n_launch),
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tflops / pk["bf16_sustained"], "traffic": None,
+                         "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the step; 97% of FLOPs)",
+                         "flops_per_step": flops, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"},
+            "clocks": sampler.result()}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        model_cpu = oracle_model(sd, cfg.to_dict(), 3129)
+        nb = 3
+        times = time_oracle(model_cpu, reqs[0], nb, 1)
+        v = B * len(times) / sum(times)
+        import torch as _t
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"{nb} forwards of batch {B} after 1 warm-up (torch fp32 oracle, "
+                                          f"{_t.get_num_threads()} threads, all heads + pre-training heads)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

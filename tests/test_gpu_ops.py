@@ -1,0 +1,203 @@
+"""Kernel-level parity through the C ABI (vb200_linear / vb200_self_attention / vb200_co_attention)
+against plain fp32 torch math on the same bf16-rounded operands.  `-m gpu` only."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from vilbert_b200 import _lib as L
+    return L, L.load()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def run_linear(x, w, bias=None, res=None, gamma=None, beta=None, act=0, block_n=0, want_bf16=True, want_f32=True,
+               ld_f32=None, pdl=0):
+    L, lib = _lib()
+    M, K = x.shape
+    N = w.shape[0]
+    dev = x.device
+    yb = torch.zeros(M, N, dtype=torch.bfloat16, device=dev) if want_bf16 and N % 8 == 0 else None
+    ldf = ld_f32 or N
+    yf = torch.full((M, ldf), float("nan"), dtype=torch.float32, device=dev) if want_f32 else None
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.vb200_linear(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(res),
+                          res.stride(0) if res is not None else 0, _ptr(gamma), _ptr(beta), 1e-12, act,
+                          _ptr(yb), N, _ptr(yf), ldf, M, N, K, block_n, pdl, C.c_void_p(stream))
+    L.check(rc, None)
+    torch.cuda.synchronize()
+    return yb, (yf[:, :N] if yf is not None else None)
+
+
+def ref_linear(x, w, bias=None, res=None, gamma=None, beta=None, act=0):
+    y = x.double() @ w.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if res is not None:
+        y = y + res.double()
+    if act == 1:
+        y = y * 0.5 * (1.0 + torch.erf(y / math.sqrt(2.0)))
+    elif act == 2:
+        y = torch.relu(y)
+    if gamma is not None:
+        u = y.mean(-1, keepdim=True)
+        s = (y - u).pow(2).mean(-1, keepdim=True)
+        y = (y - u) / torch.sqrt(s + 1e-12) * gamma.double() + beta.double()
+    return y.float()
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") * (1.0 / math.sqrt(K))).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda") * 0.1
+    return x, w, b, g
+
+
+@pytest.mark.parametrize("M,N,K,block_n", [
+    (128, 128, 64, 128),        # one tile, one k-block
+    (128, 128, 256, 128),       # k loop, ring not wrapped
+    (256, 256, 1024, 128),      # ring wraps (16 k-blocks > 6 stages)
+    (200, 384, 768, 128),       # ragged M
+    (1984, 2304, 768, 128),     # text QKV at B=64
+    (2304, 3072, 1024, 128),    # co-attention image QKV at B=64
+    (1984, 3072, 768, 256),     # wide tile
+    (77, 64, 128, 64),          # narrow tile
+    (64, 3129, 2048, 128),      # VQA logits: ragged N, M < tile
+])
+def test_linear_bias(M, N, K, block_n, parity_log):
+    x, w, b, _ = _mk(M, N, K)
+    ld = (N + 3) // 4 * 4
+    yb, yf = run_linear(x, w, b, block_n=block_n, ld_f32=ld)
+    ref = ref_linear(x, w, b)
+    err = (yf - ref).abs().max().item()
+    parity_log(test="linear_bias", M=M, N=N, K=K, block_n=block_n, max_abs_err=err, ref_std=ref.std().item())
+    assert err < 2e-3, f"fp32 output max abs err {err}"
+    if yb is not None:
+        errb = (yb.float() - ref).abs().max().item()
+        assert errb < 3e-2, f"bf16 output max abs err {errb}"
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_linear_act(act, parity_log):
+    x, w, b, _ = _mk(300, 1024, 512, seed=1)
+    _, yf = run_linear(x, w, b, act=act)
+    ref = ref_linear(x, w, b, act=act)
+    err = (yf - ref).abs().max().item()
+    parity_log(test="linear_act", act=act, max_abs_err=err)
+    assert err < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,act", [
+    (128, 128, 128, 0),         # cluster of 1
+    (300, 256, 256, 0),         # cluster of 2 (tiny config)
+    (1984, 768, 768, 0),        # text attention-output at B=64: cluster of 6 (or 96 x 8)
+    (1984, 768, 3072, 0),       # text FFN-out
+    (2304, 1024, 2112, 0),      # image embedding: cluster of 8, K with zero tail
+    (64, 2048, 1024, 1),        # SimpleClassifier: GELU then LayerNorm over 2048 = 256 x 8
+])
+def test_linear_residual_layernorm(M, N, K, act, parity_log):
+    x, w, b, g = _mk(M, N, K, seed=2)
+    res = torch.randn(M, N, generator=g, device="cuda")
+    gamma = 1.0 + 0.1 * torch.randn(N, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(N, generator=g, device="cuda")
+    yb, yf = run_linear(x, w, b, res=res, gamma=gamma, beta=beta, act=act)
+    ref = ref_linear(x, w, b, res=res, gamma=gamma, beta=beta, act=act)
+    err = (yf - ref).abs().max().item()
+    parity_log(test="linear_res_ln", M=M, N=N, K=K, max_abs_err=err)
+    assert err < 2e-3
+    assert (yb.float() - ref).abs().max().item() < 5e-2
+
+
+def test_linear_inplace_residual():
+    """LN epilogue may write its fp32 output over the residual it read (the engine's ping-pong never needs it,
+    but the kernel contract allows it)."""
+    L, lib = _lib()
+    M, N, K = 256, 256, 128
+    x, w, b, g = _mk(M, N, K, seed=3)
+    res = torch.randn(M, N, generator=g, device="cuda")
+    gamma = torch.ones(N, device="cuda")
+    beta = torch.zeros(N, device="cuda")
+    ref = ref_linear(x, w, b, res=res, gamma=gamma, beta=beta)
+    buf = res.clone()
+    rc = lib.vb200_linear(_ptr(x), K, _ptr(w), K, _ptr(b), _ptr(buf), N, _ptr(gamma), _ptr(beta), 1e-12, 0,
+                          None, 0, _ptr(buf), N, M, N, K, 0, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(rc, None)
+    torch.cuda.synchronize()
+    assert (buf - ref).abs().max().item() < 2e-3
+
+
+def test_linear_pdl_chain():
+    """Two dependent GEMMs launched with programmatic dependent launch give the same result as without."""
+    x, w, b, _ = _mk(512, 512, 512, seed=4)
+    y1, _ = run_linear(x, w, b, pdl=0)
+    y2a, _ = run_linear(x, w, b, pdl=1)
+    assert torch.equal(y1, y2a)
+
+
+def _attn_ref(q, k, v, mask_add, heads):
+    B, Lq, H = q.shape
+    Lk = k.shape[1]
+    d = H // heads
+    qh = q.float().view(B, Lq, heads, d).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Lk, heads, d).permute(0, 2, 1, 3)
+    vh = v.float().view(B, Lk, heads, d).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(d) + mask_add[:, None, None, :]
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(B, Lq, H)
+
+
+@pytest.mark.parametrize("B,L,heads,d", [(3, 31, 12, 64), (2, 38, 12, 64), (2, 36, 8, 128), (2, 101, 8, 128),
+                                         (1, 129, 2, 64), (2, 17, 2, 128)])
+def test_self_attention(B, L, heads, d, parity_log):
+    Lm, lib = _lib()
+    H = heads * d
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn(B * L, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
+    mask = torch.zeros(B, L, device="cuda")
+    mask[:, L - L // 4:] = -10000.0
+    mask[0] = 0.0
+    ctx = torch.zeros(B * L, H, dtype=torch.bfloat16, device="cuda")
+    rc = lib.vb200_self_attention(_ptr(qkv), 3 * H, H, _ptr(mask), _ptr(ctx), H, B, L, heads, d,
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    Lm.check(rc, None)
+    torch.cuda.synchronize()
+    x = qkv.view(B, L, 3 * H)
+    ref = _attn_ref(x[..., :H], x[..., H:2 * H], x[..., 2 * H:], mask, heads)
+    err = (ctx.view(B, L, H).float() - ref).abs().max().item()
+    parity_log(test="self_attention", B=B, L=L, heads=heads, d=d, max_abs_err=err)
+    assert err < 2e-2
+
+
+@pytest.mark.parametrize("B,T,V,heads,d", [(3, 31, 36, 8, 128), (2, 38, 101, 8, 128), (2, 17, 10, 2, 128),
+                                           (1, 129, 100, 8, 128)])
+def test_co_attention(B, T, V, heads, d, parity_log):
+    Lm, lib = _lib()
+    H = heads * d
+    g = torch.Generator(device="cuda").manual_seed(6)
+    qkv_i = torch.randn(B * V, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
+    qkv_t = torch.randn(B * T, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
+    mi = torch.zeros(B, V, device="cuda")
+    mi[:, V - 3:] = -10000.0
+    mt = torch.zeros(B, T, device="cuda")
+    mt[:, T - 5:] = -10000.0
+    ctx_t = torch.zeros(B * T, H, dtype=torch.bfloat16, device="cuda")
+    ctx_i = torch.zeros(B * V, H, dtype=torch.bfloat16, device="cuda")
+    rc = lib.vb200_co_attention(_ptr(qkv_i), 3 * H, _ptr(qkv_t), 3 * H, H, _ptr(mi), _ptr(mt), _ptr(ctx_t), H,
+                                _ptr(ctx_i), H, B, T, V, heads, d, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    Lm.check(rc, None)
+    torch.cuda.synchronize()
+    xi, xt = qkv_i.view(B, V, 3 * H), qkv_t.view(B, T, 3 * H)
+    ref_t = _attn_ref(xt[..., :H], xi[..., H:2 * H], xi[..., 2 * H:], mi, heads)       # text queries, image keys/values
+    ref_i = _attn_ref(xi[..., :H], xt[..., H:2 * H], xt[..., 2 * H:], mt, heads)       # image queries, text keys/values
+    e1 = (ctx_t.view(B, T, H).float() - ref_t).abs().max().item()
+    e2 = (ctx_i.view(B, V, H).float() - ref_i).abs().max().item()
+    parity_log(test="co_attention", B=B, T=T, V=V, err_text_ctx=e1, err_image_ctx=e2)
+    assert e1 < 2e-2 and e2 < 2e-2
