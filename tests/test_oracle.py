@@ -1,0 +1,129 @@
+"""The oracle itself: structure the reference pins (parameter total, tuple layout, schedule), an independent
+cross-check of the BERT layer restatement against HuggingFace transformers, and the committed golden vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vilbert_ref as R
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_parameter_count_matches_readme(full_oracle):
+    """README.md:4 of the reference: "approximately ... 270 million" parameters."""
+    n = R.count_parameters(full_oracle)
+    assert n == 268_028_859
+    assert abs(n - 270e6) / 270e6 < 0.01
+
+
+def test_schedule(full_oracle):
+    assert full_oracle.bert.encoder.schedule() == (
+        ["T0", "T1", "T2", "T3", "T4", "T5", "C0", "T6", "V0", "C1", "T7", "V1", "C2", "T8", "V2", "C3",
+         "T9", "V3", "C4", "T10", "V4", "C5", "V5", "T11"])
+
+
+def test_tuple_layout_and_odd_batch(tiny_oracle):
+    """Positional call and 10-tuple of worker.py:286-289; B odd -> element 3 is the [B,2] seq-relationship score."""
+    cfg = tiny_oracle.config
+    for B in (2, 3):
+        inp = list(R.make_inputs(B, 12, 9, seed=3, vocab_size=cfg.vocab_size))
+        inp[1] = inp[1][..., :cfg.v_feature_size].contiguous()
+        out = tiny_oracle(*inp, output_all_attention_masks=True)
+        assert len(out) == 10 and len(out[9]) == 24
+        T = 13
+        assert out[0].shape == (B, 200) and out[1].shape == (B, 1533) and out[2].shape == (B, 1)
+        assert out[3].shape == ((B // 2, 2) if B % 2 == 0 else (B, 2))
+        assert out[4].shape == (B, 3) and out[5].shape == (B, 9, cfg.v_target_size) and out[6].shape == (B, 9, 1)
+        assert out[7].shape == (B, T, cfg.vocab_size) and out[8].shape == (B, T, 1)
+
+
+def test_samples_are_independent(tiny_oracle):
+    """No cross-sample op except the NLVR2 pairing: what makes batch sharding exact."""
+    cfg = tiny_oracle.config
+    inp = list(R.make_inputs(4, 12, 9, seed=4, vocab_size=cfg.vocab_size))
+    inp[1] = inp[1][..., :cfg.v_feature_size].contiguous()
+    whole = tiny_oracle(*inp)
+    half = tiny_oracle(*[t[2:4] for t in inp])
+    for i in (0, 1, 2, 4, 6, 8):
+        assert torch.allclose(whole[i][2:4], half[i], atol=1e-5)
+    assert torch.allclose(whole[3][1:2], half[3], atol=1e-5)       # pair (2,3) is row 1 of [B/2, 2]
+
+
+def test_masks(tiny_oracle):
+    """Padding tokens / masked regions must not influence valid positions; masked regions get -10000 in vision_logit."""
+    cfg = tiny_oracle.config
+    inp = list(R.make_inputs(2, 14, 10, seed=5, vocab_size=cfg.vocab_size, pad_regions=3))
+    inp[1] = inp[1][..., :cfg.v_feature_size].contiguous()
+    a = tiny_oracle(*inp)
+    inp2 = [t.clone() for t in inp]
+    inp2[1][:, -3:] += 100.0                       # garbage in masked regions
+    pad = inp2[4] == 0
+    inp2[0][pad] = 7                               # garbage ids under padding
+    b = tiny_oracle(*inp2)
+    assert torch.allclose(a[0], b[0], atol=1e-4)
+    assert (a[6][:, -3:] < -9000).all() and (a[6][:, :-3] > -1000).all()
+
+
+def test_text_layer_matches_huggingface_bert(full_oracle):
+    """Independent pin of the BertLayer restatement: same weights through transformers' BertLayer."""
+    tr = pytest.importorskip("transformers")
+    from transformers.models.bert.modeling_bert import BertConfig as HFConfig, BertLayer as HFLayer
+    hf_cfg = HFConfig(hidden_size=768, num_attention_heads=12, intermediate_size=3072, hidden_act="gelu",
+                      layer_norm_eps=1e-12, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    try:
+        hf_cfg._attn_implementation = "eager"
+    except Exception:
+        pass
+    hf = HFLayer(hf_cfg).eval()
+    ours = full_oracle.bert.encoder.layer[3]
+    missing, unexpected = hf.load_state_dict(ours.state_dict(), strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(2, 31, 768, generator=g)
+    mask = torch.zeros(2, 1, 1, 31)
+    mask[1, ..., 20:] = -10000.0
+    with torch.no_grad():
+        ref = hf(h, attention_mask=mask)
+        ref = ref[0] if isinstance(ref, tuple) else ref
+        out, _ = ours(h, mask)
+    assert torch.allclose(out, ref, atol=2e-5), float((out - ref).abs().max())
+
+
+def test_gelu_and_layernorm_definitions():
+    x = torch.linspace(-4, 4, 101)
+    assert torch.allclose(R.gelu(x), torch.nn.functional.gelu(x), atol=1e-6)          # erf form
+    ln = R.BertLayerNorm(16)
+    y = torch.randn(3, 16)
+    assert torch.allclose(ln(y), torch.nn.functional.layer_norm(y, (16,), eps=1e-12), atol=1e-5)
+
+
+def test_golden_vectors_reproduce(full_oracle):
+    """tests/golden/*.npz were produced by tests/golden/make_golden.py from this oracle (seeded weights + inputs);
+    they must reproduce on any host (different BLAS thread counts change only the last bits)."""
+    names = {0: "vil_prediction", 1: "vil_prediction_gqa", 2: "vil_logit", 3: "vil_binary_prediction",
+             4: "vil_tri_prediction", 6: "vision_logit", 8: "linguisic_logit"}
+    files = sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    assert len(files) >= 3
+    for fn in files:
+        z = np.load(os.path.join(GOLDEN, fn))
+        inp = R.make_inputs(int(z["B"]), int(z["Tin"]), int(z["V"]), seed=int(z["seed"]), pad_regions=int(z["pad"]))
+        out = full_oracle(*inp, compute_pretraining_heads=False)
+        for i, n in names.items():
+            ref = torch.from_numpy(z[n])
+            scale = max(1.0, float(ref.abs().max()))
+            assert torch.allclose(out[i], ref, atol=2e-4 * scale), (fn, n, float((out[i] - ref).abs().max()))
+
+
+def test_synthetic_checkpoint_loads_into_oracle():
+    """The product-side key list (vilbert_b200.synthetic.state_dict_spec) == the oracle's state_dict keys/shapes."""
+    import vilbert_b200 as vb
+    from vilbert_b200 import synthetic as S
+    cfg = R.tiny_config()
+    m = R.VILBertForVLTasks(cfg, num_labels=200)
+    spec = S.state_dict_spec(vb.BertConfig.from_dict(cfg.to_dict()), num_labels=200)
+    sd = m.state_dict()
+    assert set(spec) == set(sd)
+    assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)

@@ -345,6 +345,7 @@ struct vb200_engine {
     Config cfg;
     vb200_options opt{};
     int num_labels = 0, gqa_labels = 0;
+    bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     Arena weights;
     std::string last_error;
     // embeddings
@@ -386,18 +387,21 @@ struct vb200_engine {
         return t;
     }
     float* upload_f32(const std::vector<float>& h) {
+        if (dry) return nullptr;
         float* d = weights.alloc_n<float>(h.size());
         CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
         return d;
     }
     float* load_vec(const std::string& name, int64_t n) {
         HostTensor& t = need(name, 1, n);
+        if (dry) return nullptr;
         std::vector<float> h(n);
         for (int64_t i = 0; i < n; ++i) h[i] = t.at(i);
         return upload_f32(h);
     }
     float* load_mat_f32(const std::string& name, int64_t r, int64_t c) {
         HostTensor& t = need(name, 2, r, c);
+        if (dry) return nullptr;
         std::vector<float> h(r * c);
         if (t.dtype == VB200_F32) memcpy(h.data(), t.data, h.size() * 4);
         else for (int64_t i = 0; i < r * c; ++i) h[i] = t.at(i);
@@ -416,6 +420,11 @@ struct vb200_engine {
         L.N = static_cast<int>(n_each * prefixes.size());
         L.K = static_cast<int>(k + (extra_k ? 64 : 0));
         L.ldw = (L.K + 63) / 64 * 64;
+        if (dry) {
+            for (const std::string& p : prefixes) { need(p + ".weight", 2, n_each, k); need(p + ".bias", 1, n_each); }
+            if (extra_k) { need(extra_k_prefix + ".weight", 2, n_each, extra_k); need(extra_k_prefix + ".bias", 1, n_each); }
+            return L;
+        }
         std::vector<uint16_t> h(static_cast<size_t>(L.N) * L.ldw, 0);
         std::vector<float> hb(L.N, 0.0f);
         for (size_t pi = 0; pi < prefixes.size(); ++pi) {
@@ -549,10 +558,12 @@ struct vb200_engine {
         img_decoder = load_linear1("cls.imagePredictions.decoder", c.v_target, c.v_hidden);
         {   // tied LM decoder: bf16 copy of the word-embedding table as a [vocab, hidden] GEMM operand
             HostTensor& w = need("bert.embeddings.word_embeddings.weight", 2, c.vocab, c.hidden);
-            std::vector<uint16_t> h(static_cast<size_t>(c.vocab) * c.hidden);
-            for (size_t i = 0; i < h.size(); ++i) h[i] = f32_to_bf16_bits(w.at(i));
-            word_b16 = weights.alloc_n<bf16>(h.size());
-            CUDA_CHECK(cudaMemcpy(word_b16, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+            if (!dry) {
+                std::vector<uint16_t> h(static_cast<size_t>(c.vocab) * c.hidden);
+                for (size_t i = 0; i < h.size(); ++i) h[i] = f32_to_bf16_bits(w.at(i));
+                word_b16 = weights.alloc_n<bf16>(h.size());
+                CUDA_CHECK(cudaMemcpy(word_b16, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+            }
             lm_decoder.w = word_b16; lm_decoder.bias = lm_bias; lm_decoder.N = c.vocab; lm_decoder.K = c.hidden; lm_decoder.ldw = c.hidden;
             auto it = sd.find("cls.predictions.decoder.weight");   // tied duplicate of the word table
             if (it != sd.end()) it->second.used = true;
@@ -937,6 +948,11 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         o.strict = o.strict >= 0 ? 1 : 0;
         o.use_pdl = o.use_pdl > 0 ? 1 : 0;
         Config c = parse_config(config_json);
+        {   // audit the state_dict (names, shapes, dtypes, strictness) before touching any device
+            vb200_engine audit;
+            audit.cfg = c; audit.opt = o; audit.dry = true;
+            audit.ingest(n_tensors, tensors);
+        }
         require_device(o.device);
         eng = new vb200_engine();
         eng->cfg = c;
