@@ -595,6 +595,44 @@ def build(config: Optional[RefConfig] = None, seed: int = 42, num_labels: int = 
     return model.eval()
 
 
+class emulate_activation_rounding:
+    """Context manager: run the oracle with the engine's 16-bit activation rounding points, everything else fp32.
+
+    The engine rounds (to fp16 or bf16) exactly the operands it feeds to tensor-core GEMMs -- the input of every
+    wide nn.Linear, the 5-d box operand of the image embedding included -- and the Q/K/V projections it hands to the
+    attention kernels.  The narrow heads (vil_logit, vil_tri_prediction, vision_logit, linguisic_logit,
+    bi_seq_relationship and the 2-wide last layer of vil_binary_prediction) read fp32.  With this emulation the
+    oracle becomes "what exact 16-bit arithmetic gives", so engine-vs-emulation isolates kernel bugs from the
+    unavoidable rounding of the chosen activation format.
+    """
+    NARROW = ("vil_logit", "vil_tri_prediction", "vision_logit", "linguisic_logit", "cls.bi_seq_relationship",
+              "vil_binary_prediction.logit_fc.3")
+    QKV = ("query", "key", "value", "query1", "key1", "value1", "query2", "key2", "value2")
+
+    def __init__(self, model: nn.Module, dtype: torch.dtype):
+        self.model, self.dtype, self.hooks = model, dtype, []
+
+    def __enter__(self):
+        dt = self.dtype
+
+        def pre(_mod, args):
+            return (args[0].to(dt).float(),)
+
+        def post(_mod, _args, out):
+            return out.to(dt).float()
+        for name, mod in self.model.named_modules():
+            if isinstance(mod, nn.Linear) and name not in self.NARROW:
+                self.hooks.append(mod.register_forward_pre_hook(pre))
+                if name.rsplit(".", 1)[-1] in self.QKV:
+                    self.hooks.append(mod.register_forward_hook(post))
+        return self
+
+    def __exit__(self, *exc):
+        for h in self.hooks:
+            h.remove()
+        return False
+
+
 def tiny_config(**kw) -> RefConfig:
     """A structurally identical but small model (same 12/6/6 schedule) for second-scale CPU tests."""
     d = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256,

@@ -1,0 +1,128 @@
+"""Per-kernel timing through the C ABI (CUDA events on the launching stream, after warm-up), at the shapes one
+B=64 forward launches.  Used to pick optimisation targets and, under `ncu --set full`, to read stall reasons.
+
+    python scripts/kernel_bench.py [--only NAME] [--reps 50] [--batch 64]
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vilbert_b200 import _lib as L
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--act", default="fp16")
+    ap.add_argument("--sets", type=int, default=4, help="operand sets cycled through per kernel")
+    a = ap.parse_args()
+    lib = L.load()
+    B, T, V = a.batch, 31, 36
+    Mt, Mv = B * T, B * V
+    act = torch.float16 if a.act == "fp16" else torch.bfloat16
+    f16 = 1 if a.act == "fp16" else 0
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(0)
+    # name, M, N, K, act, residual+LN, block_n
+    gemms = [
+        ("text_qkv", Mt, 2304, 768, 0, False, 0), ("text_attn_out_ln", Mt, 768, 768, 0, True, 0),
+        ("text_ffn_in_gelu", Mt, 3072, 768, 1, False, 0), ("text_ffn_out_ln", Mt, 768, 3072, 0, True, 0),
+        ("img_qkv", Mv, 3072, 1024, 0, False, 0), ("img_attn_out_ln", Mv, 1024, 1024, 0, True, 0),
+        ("img_ffn_in_gelu", Mv, 1024, 1024, 1, False, 0), ("img_embed_ln", Mv, 1024, 2112, 0, True, 0),
+        ("co_txt_qkv", Mt, 3072, 768, 0, False, 0), ("co_dense2_ln", Mt, 768, 1024, 0, True, 0),
+        ("text_ffn_in_gelu_bn256", Mt, 3072, 768, 1, False, 256), ("pool_t", B, 1024, 768, 2, False, 0),
+        ("vqa_fc0_gelu_ln", B, 2048, 1024, 1, True, 0), ("vqa_fc3", B, 3129, 2048, 0, False, 0),
+    ]
+    res = []
+    for name, M, N, K, actf, ln, bn in gemms:
+        if a.only and a.only not in name:
+            continue
+        sets = []
+        for _ in range(a.sets):
+            x = torch.randn(M, K, generator=g, device="cuda").to(act)
+            w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+            b = torch.randn(N, generator=g, device="cuda")
+            r = torch.randn(M, N, generator=g, device="cuda") if ln else None
+            ga = torch.ones(N, device="cuda") if ln else None
+            be = torch.zeros(N, device="cuda") if ln else None
+            ldf = (N + 3) // 4 * 4
+            yb = torch.empty(M, N, dtype=act, device="cuda") if N % 8 == 0 else None
+            yf = torch.empty(M, ldf, device="cuda") if (ln or N % 8) else None
+            sets.append((x, w, b, r, ga, be, yb, yf, ldf))
+
+        def run(i):
+            x, w, b, r, ga, be, yb, yf, ldf = sets[i % a.sets]
+            rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
+                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, C.c_void_p(st))
+            L.check(rc, None)
+        for i in range(5):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.reps):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / a.reps
+        fl = 2.0 * M * N * K
+        res.append(dict(kernel=name, M=M, N=N, K=K, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
+        print(json.dumps(res[-1]), flush=True)
+
+    attn = [("self_attn_text", 12, 64, T), ("self_attn_img", 8, 128, V)]
+    for name, heads, d, Lq in attn:
+        if a.only and a.only not in name:
+            continue
+        H = heads * d
+        qkv = torch.randn(B * Lq, 3 * H, generator=g, device="cuda").to(act)
+        mask = torch.zeros(B, Lq, device="cuda")
+        ctx = torch.empty(B * Lq, H, dtype=act, device="cuda")
+
+        def run(i):
+            L.check(lib.vb200_self_attention(ptr(qkv), 3 * H, H, ptr(mask), ptr(ctx), H, B, Lq, heads, d, f16, C.c_void_p(st)), None)
+        for i in range(5):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.reps):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / a.reps
+        print(json.dumps(dict(kernel=name, us=round(us, 2))), flush=True)
+    if not a.only or "co_attn" in a.only:
+        H = 1024
+        qi = torch.randn(Mv, 3 * H, generator=g, device="cuda").to(act)
+        qt = torch.randn(Mt, 3 * H, generator=g, device="cuda").to(act)
+        mi, mt = torch.zeros(B, V, device="cuda"), torch.zeros(B, T, device="cuda")
+        ct, ci = torch.empty(Mt, H, dtype=act, device="cuda"), torch.empty(Mv, H, dtype=act, device="cuda")
+
+        def run(i):
+            L.check(lib.vb200_co_attention(ptr(qi), 3 * H, ptr(qt), 3 * H, H, ptr(mi), ptr(mt), ptr(ct), H, ptr(ci), H,
+                                           B, T, V, 8, 128, f16, C.c_void_p(st)), None)
+        for i in range(5):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.reps):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps(dict(kernel="co_attn", us=round(e0.elapsed_time(e1) * 1e3 / a.reps, 2))), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,22 +1,34 @@
-"""End-to-end parity of the CUDA engine (through the worker-facing Python protocol -> C ABI) against the
+"""End-to-end parity of the CUDA engine (worker-facing Python protocol -> C ABI -> sm_100a kernels) against the
 fp32 CPU oracle on identical seeded inputs.  `-m gpu` only.
 
-Tolerance: BASELINE.json's north_star asks for 1e-2 per logit in bf16.  The engine computes with bf16 GEMM
-operands / fp32 accumulation, fp32 residual stream and LayerNorm statistics; the synthetic checkpoint is
-bf16-representable (oracle.init_weights(bf16_exact=True)) so both sides start from identical parameters and
-the measured error is purely the engine's arithmetic.  Measured numbers are appended to
-gpurun_out/parity.jsonl.
+Tolerances (BASELINE.json north_star: "within 1e-3 fp32 / 1e-2 bf16 per logit"):
+
+* TOL = 1e-2 per logit against the fp32 oracle -- met by the DEFAULT engine mode (bf16 weights x fp16 activations,
+  fp32 accumulation / residual stream / LayerNorm / softmax).
+* The pure-bf16-activation mode (act_dtype="bf16") cannot meet 1e-2 against fp32: rounding the ~150 GEMM operands of
+  this network to an 8-bit significand moves the VQA logits (std 0.91) by up to ~1.9e-2 in *exact* arithmetic --
+  the oracle itself shows it when its activations are rounded to bf16 at the same points
+  (oracle.emulate_activation_rounding; tests/test_oracle.py pins that number on CPU).  That mode is therefore checked
+  (a) against the fp32 oracle at TOL_BF16_VS_FP32 = 2.5e-2 and (b) against the bf16-rounding oracle at TOL_EMUL,
+  which isolates kernel correctness from the format's rounding.
+
+The synthetic checkpoint is bf16-representable (oracle.init_weights(bf16_exact=True)), so both sides start from
+identical parameters.  Measured numbers are appended to gpurun_out/parity.jsonl.
 """
-import numpy as np
 import os
+
+import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL_BF16 = 1e-2          # per logit, families with O(1) spread (north_star)
+TOL = 1e-2                 # north_star, default mode vs fp32 oracle
+TOL_BF16_VS_FP32 = 2.5e-2  # bf16-activation mode vs fp32 oracle (format floor ~1.9e-2, see module docstring)
+TOL_EMUL = 5e-3            # either mode vs the oracle with the same 16-bit rounding points
 NAMES = ["vil_prediction", "vil_prediction_gqa", "vil_logit", "vil_binary_prediction", "vil_tri_prediction",
          "vision_prediction", "vision_logit", "linguisic_prediction", "linguisic_logit"]
+DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 
 
 def _engine(oracle, **kw):
@@ -28,65 +40,81 @@ def _engine(oracle, **kw):
 
 
 @pytest.fixture(scope="module")
-def tiny_engine(tiny_oracle):
-    m = _engine(tiny_oracle)
-    yield m
-    m.close()
+def tiny_engines(tiny_oracle):
+    e = {k: _engine(tiny_oracle, act_dtype=k) for k in DT}
+    yield e
+    for m in e.values():
+        m.close()
 
 
 @pytest.fixture(scope="module")
-def full_engine(full_oracle):
-    m = _engine(full_oracle)
-    yield m
-    m.close()
+def full_engines(full_oracle):
+    e = {k: _engine(full_oracle, act_dtype=k) for k in DT}
+    yield e
+    for m in e.values():
+        m.close()
 
 
-def _compare(oracle, engine, inputs, parity_log, tag, tol, pretraining=True, taps=False):
-    ref = oracle(*inputs, output_all_attention_masks=False, compute_pretraining_heads=pretraining)
-    dev = [t.cuda() for t in inputs]
-    out = engine(*dev, output_all_attention_masks=True, compute_pretraining_heads=pretraining)
-    torch.cuda.synchronize()
-    worst = 0.0
+def _errs(ref, out):
+    """max abs error per output, ignoring the -10000 rows of masked regions (checked on a relative scale)."""
+    res = {}
     for i, name in enumerate(NAMES):
         r, o = ref[i], out[i]
         if r is None:
-            assert o is None
+            assert o is None, name
             continue
-        assert o is not None, name
-        assert tuple(o.shape) == tuple(r.shape), (name, o.shape, r.shape)
-        # padded regions carry -10000 in vision_logit: compare them exactly-ish on relative scale
+        assert o is not None and tuple(o.shape) == tuple(r.shape), (name, None if o is None else o.shape, r.shape)
         diff = (o.cpu() - r).abs()
         big = r.abs() > 1000
-        err = float(diff[~big].max()) if (~big).any() else 0.0
         if big.any():
-            assert float((diff[big] / r[big].abs()).max()) < 1e-3
-        parity_log(test=tag, output=name, max_abs_err=err, ref_std=float(r[~big].std()) if (~big).sum() > 1 else 0.0,
-                   shape=list(r.shape))
-        worst = max(worst, err)
-        assert err < tol, f"{tag}: {name} max abs err {err} >= {tol}"
-    assert out[9] == []
-    return worst
+            assert float((diff[big] / r[big].abs()).max()) < 1e-3, name
+        res[name] = (float(diff[~big].max()) if (~big).any() else 0.0, float(r[~big].std()) if (~big).sum() > 1 else 0.0)
+    return res
 
 
-@pytest.mark.parametrize("B,Tin,V,pad", [(2, 30, 36, 0), (3, 16, 10, 3), (4, 37, 101, 7), (1, 12, 37, 0)])
-def test_tiny_model_all_outputs(tiny_oracle, tiny_engine, parity_log, B, Tin, V, pad):
+def _check(oracle, engines, inputs, parity_log, tag, pretraining):
     from oracle import vilbert_ref as R
-    inp = R.make_inputs(B, Tin, V, seed=100 + B, vocab_size=tiny_oracle.config.vocab_size, pad_regions=pad)
-    inp = list(inp)
-    inp[1] = inp[1][..., :tiny_oracle.config.v_feature_size].contiguous()
-    _compare(tiny_oracle, tiny_engine, inp, parity_log, f"tiny_B{B}_T{Tin}_V{V}", TOL_BF16)
+    ref32 = oracle(*inputs, compute_pretraining_heads=pretraining)
+    dev = [t.cuda() for t in inputs]
+    for mode, eng in engines.items():
+        out = eng(*dev, output_all_attention_masks=True, compute_pretraining_heads=pretraining)
+        torch.cuda.synchronize()
+        assert out[9] == []
+        with R.emulate_activation_rounding(oracle, DT[mode]):
+            ref_em = oracle(*inputs, compute_pretraining_heads=pretraining)
+        e32, eem = _errs(ref32, out), _errs(ref_em, out)
+        tol32 = TOL if mode == "fp16" else TOL_BF16_VS_FP32
+        for name in e32:
+            parity_log(test=tag, mode=mode, output=name, err_vs_fp32=e32[name][0], err_vs_emulated=eem[name][0],
+                       ref_std=e32[name][1])
+        for name in e32:
+            assert e32[name][0] < tol32, f"{tag}/{mode}: {name} vs fp32 oracle: {e32[name][0]} >= {tol32}"
+            assert eem[name][0] < TOL_EMUL, f"{tag}/{mode}: {name} vs {mode}-rounding oracle: {eem[name][0]} >= {TOL_EMUL}"
 
 
-def test_tiny_model_eager_equals_graph(tiny_oracle, tiny_engine):
+def _tiny_inputs(oracle, B, Tin, V, seed, pad=0):
+    from oracle import vilbert_ref as R
+    inp = list(R.make_inputs(B, Tin, V, seed=seed, vocab_size=oracle.config.vocab_size, pad_regions=pad))
+    inp[1] = inp[1][..., :oracle.config.v_feature_size].contiguous()
+    return inp
+
+
+@pytest.mark.parametrize("B,Tin,V,pad", [(2, 30, 36, 0), (3, 16, 10, 3), (4, 37, 101, 7), (1, 12, 37, 0), (2, 128, 100, 0)])
+def test_tiny_model_all_outputs(tiny_oracle, tiny_engines, parity_log, B, Tin, V, pad):
+    """Structurally complete 12/6/6 model at reduced width: all nine outputs incl. the pre-training heads, ragged text
+    lengths, masked regions, odd batch (binary head falls back to the seq-relationship score), and the corner of the
+    BASELINE sweep (text 128, regions 100)."""
+    _check(tiny_oracle, tiny_engines, _tiny_inputs(tiny_oracle, B, Tin, V, 100 + B, pad), parity_log,
+           f"tiny_B{B}_T{Tin}_V{V}", pretraining=True)
+
+
+def test_tiny_model_eager_equals_graph(tiny_oracle, tiny_engines):
     """CUDA-graph replay and eager launches of the same plan give bit-identical outputs."""
-    from oracle import vilbert_ref as R
-    inp = list(R.make_inputs(2, 20, 12, seed=5, vocab_size=tiny_oracle.config.vocab_size))
-    inp[1] = inp[1][..., :tiny_oracle.config.v_feature_size].contiguous()
-    dev = [t.cuda() for t in inp]
+    dev = [t.cuda() for t in _tiny_inputs(tiny_oracle, 2, 20, 12, 5)]
     eager = _engine(tiny_oracle, use_cuda_graph=False)
-    a = tiny_engine(*dev)
+    a = tiny_engines["fp16"](*dev)
     b = eager(*dev)
-    c = tiny_engine(*dev)
+    c = tiny_engines["fp16"](*dev)
     torch.cuda.synchronize()
     for x, y, z in zip(a[:9], b[:9], c[:9]):
         if x is not None:
@@ -94,14 +122,11 @@ def test_tiny_model_eager_equals_graph(tiny_oracle, tiny_engine):
     eager.close()
 
 
-def test_tiny_model_pdl(tiny_oracle, tiny_engine):
+def test_tiny_model_pdl(tiny_oracle, tiny_engines):
     """Programmatic dependent launch changes scheduling only, never results."""
-    from oracle import vilbert_ref as R
-    inp = list(R.make_inputs(2, 20, 12, seed=6, vocab_size=tiny_oracle.config.vocab_size))
-    inp[1] = inp[1][..., :tiny_oracle.config.v_feature_size].contiguous()
-    dev = [t.cuda() for t in inp]
+    dev = [t.cuda() for t in _tiny_inputs(tiny_oracle, 2, 20, 12, 6)]
     pdl = _engine(tiny_oracle, use_pdl=True)
-    a = tiny_engine(*dev)
+    a = tiny_engines["fp16"](*dev)
     b = pdl(*dev)
     torch.cuda.synchronize()
     for x, y in zip(a[:9], b[:9]):
@@ -110,21 +135,34 @@ def test_tiny_model_pdl(tiny_oracle, tiny_engine):
     pdl.close()
 
 
+def test_tiny_model_host_api(tiny_oracle, tiny_engines):
+    """vb200_forward_host (pinned host buffers in/out) == vb200_forward (device pointers)."""
+    from vilbert_b200 import _lib as L
+    inp = _tiny_inputs(tiny_oracle, 4, 20, 12, 8)
+    eng = tiny_engines["fp16"]
+    ref = eng(*[t.cuda() for t in inp])
+    hin = [t.pin_memory() for i, t in enumerate(inp) if i != 6]
+    out = {"vil_prediction": torch.empty(4, tiny_oracle.num_labels).pin_memory(),
+           "vision_logit": torch.empty(4, 12, 1).pin_memory()}
+    eng.forward_host(*hin, out, select=L.OUT_VIL_PREDICTION | L.OUT_VISION_LOGIT)
+    assert torch.equal(out["vil_prediction"], ref[0].cpu()) and torch.equal(out["vision_logit"], ref[6].cpu())
+
+
 @pytest.mark.parametrize("B,Tin,V,pad", [(1, 30, 36, 0), (2, 30, 36, 0), (3, 37, 101, 5), (2, 16, 10, 0)])
-def test_full_model_task_heads(full_oracle, full_engine, parity_log, B, Tin, V, pad):
+def test_full_model_task_heads(full_oracle, full_engines, parity_log, B, Tin, V, pad):
     from oracle import vilbert_ref as R
     inp = R.make_inputs(B, Tin, V, seed=1234 + B, pad_regions=pad)
-    _compare(full_oracle, full_engine, inp, parity_log, f"full_B{B}_T{Tin}_V{V}", TOL_BF16, pretraining=False)
+    _check(full_oracle, full_engines, inp, parity_log, f"full_B{B}_T{Tin}_V{V}", pretraining=False)
 
 
-def test_full_model_pretraining_heads(full_oracle, full_engine, parity_log):
+def test_full_model_pretraining_heads(full_oracle, full_engines, parity_log):
     from oracle import vilbert_ref as R
     inp = R.make_inputs(2, 30, 36, seed=77)
-    _compare(full_oracle, full_engine, inp, parity_log, "full_pretraining", TOL_BF16, pretraining=True)
+    _check(full_oracle, full_engines, inp, parity_log, "full_pretraining", pretraining=True)
 
 
-def test_full_model_golden(full_engine, parity_log):
-    """Committed fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle)."""
+def test_full_model_golden(full_engines, parity_log):
+    """Committed fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the fp32 oracle)."""
     from oracle import vilbert_ref as R
     gdir = os.path.join(os.path.dirname(__file__), "golden")
     files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
@@ -133,7 +171,7 @@ def test_full_model_golden(full_engine, parity_log):
         z = np.load(os.path.join(gdir, fn))
         B, Tin, V, seed, pad = (int(z[k]) for k in ("B", "Tin", "V", "seed", "pad"))
         inp = R.make_inputs(B, Tin, V, seed=seed, pad_regions=pad)
-        out = full_engine(*[t.cuda() for t in inp])
+        out = full_engines["fp16"](*[t.cuda() for t in inp])
         torch.cuda.synchronize()
         for i, name in enumerate(NAMES):
             if name in z.files:
@@ -141,24 +179,25 @@ def test_full_model_golden(full_engine, parity_log):
                 small = r.abs() < 1000
                 err = float((out[i].cpu() - r).abs()[small].max())
                 parity_log(test="golden:" + fn, output=name, max_abs_err=err)
-                assert err < TOL_BF16, (fn, name, err)
+                assert err < TOL, (fn, name, err)
 
 
-def test_batch64_shard_equivalence(full_oracle, full_engine, parity_log):
+def test_batch64_shard_equivalence(full_oracle, full_engines, parity_log):
     """Full-size property: a pair's logits do not depend on what else is in the batch --
-    B=64 in one call == the same 64 pairs in 4 calls of 16 (what batch sharding over ranks does)."""
+    B=64 in one call == the same 64 pairs in 4 calls of 16 (what batch sharding over ranks does), bit for bit;
+    plus a spot check of 4 of the 64 rows against the oracle (BASELINE.json configs[1] shape)."""
     from oracle import vilbert_ref as R
+    eng = full_engines["fp16"]
     inp = R.make_inputs(64, 30, 36, seed=4321, full_masks=False)
     dev = [t.cuda() for t in inp]
-    whole = full_engine(*dev)[0]
-    parts = torch.cat([full_engine(*[t[i:i + 16] for t in dev])[0] for i in range(0, 64, 16)])
+    whole = eng(*dev)[0]
+    parts = torch.cat([eng(*[t[i:i + 16] for t in dev])[0] for i in range(0, 64, 16)])
     torch.cuda.synchronize()
     d = float((whole - parts).abs().max())
     parity_log(test="batch64_shard_equivalence", max_abs_diff=d)
     assert d == 0.0
-    # and a spot check of 4 of the 64 rows against the oracle
     idx = [0, 21, 42, 63]
     ref = full_oracle(*[t[idx] for t in inp], compute_pretraining_heads=False)[0]
     err = float((whole[idx].cpu() - ref).abs().max())
     parity_log(test="batch64_rows_vs_oracle", max_abs_err=err, ref_std=float(ref.std()))
-    assert err < TOL_BF16
+    assert err < TOL

@@ -20,17 +20,19 @@ def _ptr(t):
 
 def run_linear(x, w, bias=None, res=None, gamma=None, beta=None, act=0, block_n=0, want_bf16=True, want_f32=True,
                ld_f32=None, pdl=0):
+    """x: fp16 or bf16 activations (the 16-bit output has the same format); w: bf16 weights."""
     L, lib = _lib()
     M, K = x.shape
     N = w.shape[0]
     dev = x.device
-    yb = torch.zeros(M, N, dtype=torch.bfloat16, device=dev) if want_bf16 and N % 8 == 0 else None
+    f16 = 1 if x.dtype == torch.float16 else 0
+    yb = torch.zeros(M, N, dtype=x.dtype, device=dev) if want_bf16 and N % 8 == 0 else None
     ldf = ld_f32 or N
     yf = torch.full((M, ldf), float("nan"), dtype=torch.float32, device=dev) if want_f32 else None
     stream = torch.cuda.current_stream().cuda_stream
     rc = lib.vb200_linear(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(res),
                           res.stride(0) if res is not None else 0, _ptr(gamma), _ptr(beta), 1e-12, act,
-                          _ptr(yb), N, _ptr(yf), ldf, M, N, K, block_n, pdl, C.c_void_p(stream))
+                          _ptr(yb), N, _ptr(yf), ldf, M, N, K, block_n, pdl, f16, C.c_void_p(stream))
     L.check(rc, None)
     torch.cuda.synchronize()
     return yb, (yf[:, :N] if yf is not None else None)
@@ -53,9 +55,12 @@ def ref_linear(x, w, bias=None, res=None, gamma=None, beta=None, act=0):
     return y.float()
 
 
-def _mk(M, N, K, seed=0):
+ACT = [torch.float16, torch.bfloat16]
+
+
+def _mk(M, N, K, seed=0, act=torch.bfloat16):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    x = torch.randn(M, K, generator=g, device="cuda").to(act)
     w = (torch.randn(N, K, generator=g, device="cuda") * (1.0 / math.sqrt(K))).to(torch.bfloat16)
     b = torch.randn(N, generator=g, device="cuda") * 0.1
     return x, w, b, g
@@ -72,22 +77,24 @@ def _mk(M, N, K, seed=0):
     (77, 64, 128, 64),          # narrow tile
     (64, 3129, 2048, 128),      # VQA logits: ragged N, M < tile
 ])
-def test_linear_bias(M, N, K, block_n, parity_log):
-    x, w, b, _ = _mk(M, N, K)
+@pytest.mark.parametrize("act_dt", ACT)
+def test_linear_bias(M, N, K, block_n, act_dt, parity_log):
+    x, w, b, _ = _mk(M, N, K, act=act_dt)
     ld = (N + 3) // 4 * 4
     yb, yf = run_linear(x, w, b, block_n=block_n, ld_f32=ld)
     ref = ref_linear(x, w, b)
     err = (yf - ref).abs().max().item()
-    parity_log(test="linear_bias", M=M, N=N, K=K, block_n=block_n, max_abs_err=err, ref_std=ref.std().item())
+    parity_log(test="linear_bias", M=M, N=N, K=K, block_n=block_n, act=str(act_dt), max_abs_err=err, ref_std=ref.std().item())
     assert err < 2e-3, f"fp32 output max abs err {err}"
     if yb is not None:
         errb = (yb.float() - ref).abs().max().item()
         assert errb < 3e-2, f"bf16 output max abs err {errb}"
 
 
+@pytest.mark.parametrize("act_dt", ACT)
 @pytest.mark.parametrize("act", [1, 2])
-def test_linear_act(act, parity_log):
-    x, w, b, _ = _mk(300, 1024, 512, seed=1)
+def test_linear_act(act, act_dt, parity_log):
+    x, w, b, _ = _mk(300, 1024, 512, seed=1, act=act_dt)
     _, yf = run_linear(x, w, b, act=act)
     ref = ref_linear(x, w, b, act=act)
     err = (yf - ref).abs().max().item()
@@ -103,8 +110,9 @@ def test_linear_act(act, parity_log):
     (2304, 1024, 2112, 0),      # image embedding: cluster of 8, K with zero tail
     (64, 2048, 1024, 1),        # SimpleClassifier: GELU then LayerNorm over 2048 = 256 x 8
 ])
-def test_linear_residual_layernorm(M, N, K, act, parity_log):
-    x, w, b, g = _mk(M, N, K, seed=2)
+@pytest.mark.parametrize("act_dt", ACT)
+def test_linear_residual_layernorm(M, N, K, act, act_dt, parity_log):
+    x, w, b, g = _mk(M, N, K, seed=2, act=act_dt)
     res = torch.randn(M, N, generator=g, device="cuda")
     gamma = 1.0 + 0.1 * torch.randn(N, generator=g, device="cuda")
     beta = 0.1 * torch.randn(N, generator=g, device="cuda")
@@ -128,7 +136,7 @@ def test_linear_inplace_residual():
     ref = ref_linear(x, w, b, res=res, gamma=gamma, beta=beta)
     buf = res.clone()
     rc = lib.vb200_linear(_ptr(x), K, _ptr(w), K, _ptr(b), _ptr(buf), N, _ptr(gamma), _ptr(beta), 1e-12, 0,
-                          None, 0, _ptr(buf), N, M, N, K, 0, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                          None, 0, _ptr(buf), N, M, N, K, 0, 0, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     L.check(rc, None)
     torch.cuda.synchronize()
     assert (buf - ref).abs().max().item() < 2e-3
@@ -154,19 +162,20 @@ def _attn_ref(q, k, v, mask_add, heads):
     return (p @ vh).permute(0, 2, 1, 3).reshape(B, Lq, H)
 
 
+@pytest.mark.parametrize("act_dt", ACT)
 @pytest.mark.parametrize("B,L,heads,d", [(3, 31, 12, 64), (2, 38, 12, 64), (2, 36, 8, 128), (2, 101, 8, 128),
                                          (1, 129, 2, 64), (2, 17, 2, 128)])
-def test_self_attention(B, L, heads, d, parity_log):
+def test_self_attention(B, L, heads, d, act_dt, parity_log):
     Lm, lib = _lib()
     H = heads * d
     g = torch.Generator(device="cuda").manual_seed(5)
-    qkv = torch.randn(B * L, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
+    qkv = torch.randn(B * L, 3 * H, generator=g, device="cuda").to(act_dt)
     mask = torch.zeros(B, L, device="cuda")
     mask[:, L - L // 4:] = -10000.0
     mask[0] = 0.0
-    ctx = torch.zeros(B * L, H, dtype=torch.bfloat16, device="cuda")
+    ctx = torch.zeros(B * L, H, dtype=act_dt, device="cuda")
     rc = lib.vb200_self_attention(_ptr(qkv), 3 * H, H, _ptr(mask), _ptr(ctx), H, B, L, heads, d,
-                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                  1 if act_dt == torch.float16 else 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     Lm.check(rc, None)
     torch.cuda.synchronize()
     x = qkv.view(B, L, 3 * H)
@@ -176,22 +185,24 @@ def test_self_attention(B, L, heads, d, parity_log):
     assert err < 2e-2
 
 
+@pytest.mark.parametrize("act_dt", ACT)
 @pytest.mark.parametrize("B,T,V,heads,d", [(3, 31, 36, 8, 128), (2, 38, 101, 8, 128), (2, 17, 10, 2, 128),
                                            (1, 129, 100, 8, 128)])
-def test_co_attention(B, T, V, heads, d, parity_log):
+def test_co_attention(B, T, V, heads, d, act_dt, parity_log):
     Lm, lib = _lib()
     H = heads * d
     g = torch.Generator(device="cuda").manual_seed(6)
-    qkv_i = torch.randn(B * V, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
-    qkv_t = torch.randn(B * T, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
+    qkv_i = torch.randn(B * V, 3 * H, generator=g, device="cuda").to(act_dt)
+    qkv_t = torch.randn(B * T, 3 * H, generator=g, device="cuda").to(act_dt)
     mi = torch.zeros(B, V, device="cuda")
     mi[:, V - 3:] = -10000.0
     mt = torch.zeros(B, T, device="cuda")
     mt[:, T - 5:] = -10000.0
-    ctx_t = torch.zeros(B * T, H, dtype=torch.bfloat16, device="cuda")
-    ctx_i = torch.zeros(B * V, H, dtype=torch.bfloat16, device="cuda")
+    ctx_t = torch.zeros(B * T, H, dtype=act_dt, device="cuda")
+    ctx_i = torch.zeros(B * V, H, dtype=act_dt, device="cuda")
     rc = lib.vb200_co_attention(_ptr(qkv_i), 3 * H, _ptr(qkv_t), 3 * H, H, _ptr(mi), _ptr(mt), _ptr(ctx_t), H,
-                                _ptr(ctx_i), H, B, T, V, heads, d, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                _ptr(ctx_i), H, B, T, V, heads, d, 1 if act_dt == torch.float16 else 0,
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
     Lm.check(rc, None)
     torch.cuda.synchronize()
     xi, xt = qkv_i.view(B, V, 3 * H), qkv_t.view(B, T, 3 * H)

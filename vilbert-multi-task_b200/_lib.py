@@ -51,7 +51,7 @@ class Outputs(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_labels", C.c_int32), ("use_cuda_graph", C.c_int32),
-                ("use_pdl", C.c_int32), ("strict", C.c_int32)]
+                ("use_pdl", C.c_int32), ("strict", C.c_int32), ("act_fp16", C.c_int32)]
 
 
 # every symbol include/vilbert_b200.h declares (tests/test_cabi.py checks the list against the header)
@@ -90,9 +90,9 @@ def load():
     lib.vb200_plan_info.argtypes = [vp, i32, i32, i32, u32, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb200_model_dim.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     lib.vb200_linear.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, f32, i32, vp, i64, vp, i64,
-                                 i64, i64, i64, i32, i32, vp]
-    lib.vb200_self_attention.argtypes = [vp, i64, i32, vp, vp, i64, i32, i32, i32, i32, vp]
-    lib.vb200_co_attention.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
+                                 i64, i64, i64, i32, i32, i32, vp]
+    lib.vb200_self_attention.argtypes = [vp, i64, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp]
+    lib.vb200_co_attention.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("vb200_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -38,7 +38,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
 
 // One warp per query row.  Qs/Ks/Vs: padded bf16 tiles.  mask_add[j] additive key mask (fp32).
 // out: bf16 global, row stride ld_out, already offset to this head's first column.
-template <int D>
+template <int D, bool F16>
 __device__ __forceinline__ void attend_rows(const __nv_bfloat16* Qs, const __nv_bfloat16* Ks, const __nv_bfloat16* Vs,
                                             int nq, int nk, const float* mask_add, float scale, float* p_warp,
                                             __nv_bfloat16* out, int ld_out, int warp, int nwarps, int lane) {
@@ -57,8 +57,8 @@ __device__ __forceinline__ void attend_rows(const __nv_bfloat16* Qs, const __nv_
                     float acc = 0.0f;
 #pragma unroll 8
                     for (int k2 = 0; k2 < D / 2; ++k2) {
-                        const float2 q = unpack_bf16x2(qrow[k2]);
-                        const float2 k = unpack_bf16x2(krow[k2]);
+                        const float2 q = unpack16x2<F16>(qrow[k2]);
+                        const float2 k = unpack16x2<F16>(krow[k2]);
                         acc = fmaf(q.x, k.x, acc);
                         acc = fmaf(q.y, k.y, acc);
                     }
@@ -97,19 +97,19 @@ __device__ __forceinline__ void attend_rows(const __nv_bfloat16* Qs, const __nv_
             const uint32_t* vrow = reinterpret_cast<const uint32_t*>(Vs + j * kStride);
 #pragma unroll
             for (int cc = 0; cc < D / 64; ++cc) {
-                const float2 v = unpack_bf16x2(vrow[lane + 32 * cc]);
+                const float2 v = unpack16x2<F16>(vrow[lane + 32 * cc]);
                 acc[cc].x = fmaf(pj, v.x, acc[cc].x);
                 acc[cc].y = fmaf(pj, v.y, acc[cc].y);
             }
         }
         uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<size_t>(i) * ld_out);
 #pragma unroll
-        for (int cc = 0; cc < D / 64; ++cc) orow[lane + 32 * cc] = pack_bf16x2(acc[cc].x, acc[cc].y);
+        for (int cc = 0; cc < D / 64; ++cc) orow[lane + 32 * cc] = pack16x2<F16>(acc[cc].x, acc[cc].y);
         __syncwarp();   // p_warp reused by the next row
     }
 }
 
-template <int D>
+template <int D, bool F16>
 __global__ void __launch_bounds__(128)
 self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int hidden,
                       const float* __restrict__ key_mask_add, __nv_bfloat16* __restrict__ ctx, int ld_ctx, int L,
@@ -132,11 +132,11 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int hid
     load_tile<D>(Vs, base + 2 * hidden, L, ld_qkv);
     for (int j = threadIdx.x; j < L; j += blockDim.x) mask_s[j] = key_mask_add[b * L + j];
     __syncthreads();
-    attend_rows<D>(Qs, Ks, Vs, L, L, mask_s, scale, p_all + warp * L,
+    attend_rows<D, F16>(Qs, Ks, Vs, L, L, mask_s, scale, p_all + warp * L,
                    ctx + static_cast<size_t>(b) * L * ld_ctx + h * D, ld_ctx, warp, nwarps, lane);
 }
 
-template <int D>
+template <int D, bool F16>
 __global__ void __launch_bounds__(256)
 co_attention_kernel(const __nv_bfloat16* __restrict__ qkv_img, int ld_img, const __nv_bfloat16* __restrict__ qkv_txt,
                     int ld_txt, int hidden, const float* __restrict__ img_mask_add,
@@ -172,37 +172,54 @@ co_attention_kernel(const __nv_bfloat16* __restrict__ qkv_img, int ld_img, const
     for (int j = threadIdx.x; j < T; j += blockDim.x) mask_txt[j] = txt_mask_add[b * T + j];
     __syncthreads();
     // text queries over image keys/values -> context for the text stream
-    attend_rows<D>(Q2, K1, V1, T, V, mask_img, scale, p_all + warp * maxk,
+    attend_rows<D, F16>(Q2, K1, V1, T, V, mask_img, scale, p_all + warp * maxk,
                    ctx_txt + static_cast<size_t>(b) * T * ld_ctx_txt + h * D, ld_ctx_txt, warp, nwarps, lane);
     // image queries over text keys/values -> context for the image stream
-    attend_rows<D>(Q1, K2, V2, V, T, mask_txt, scale, p_all + warp * maxk,
+    attend_rows<D, F16>(Q1, K2, V2, V, T, mask_txt, scale, p_all + warp * maxk,
                    ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D, ld_ctx_img, warp, nwarps, lane);
+}
+
+template <int D, bool F16>
+static cudaError_t launch_self(const __nv_bfloat16* qkv, int ld_qkv, int hidden, const float* key_mask_add,
+                               __nv_bfloat16* ctx, int ld_ctx, int B, int L, int heads, float scale, size_t smem, int pdl,
+                               cudaStream_t st) {
+    cudaError_t e = set_smem(self_attention_kernel<D, F16>, smem);
+    if (e != cudaSuccess) return e;
+    return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(128), smem, pdl, st, qkv, ld_qkv, hidden,
+                     key_mask_add, ctx, ld_ctx, L, scale, pdl);
 }
 
 cudaError_t launch_self_attention(const __nv_bfloat16* qkv, int ld_qkv, int hidden, const float* key_mask_add,
                                   __nv_bfloat16* ctx, int ld_ctx, int B, int L, int heads, int head_dim, int pdl,
-                                  cudaStream_t st) {
+                                  int f16, cudaStream_t st) {
     if (L > 32 * kMaxKeyChunks || (head_dim != 64 && head_dim != 128) || (ld_qkv & 7) || (ld_ctx & 1) || (hidden & 7))
         return cudaErrorInvalidValue;
     const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
     const int nwarps = 4;
     const size_t stride = head_dim + 2;
     const size_t smem = 3 * L * stride * 2 + 4 + sizeof(float) * (L + nwarps * L);
-    cudaError_t e;
-    if (head_dim == 64) {
-        if ((e = set_smem(self_attention_kernel<64>, smem)) != cudaSuccess) return e;
-        return launch_ex(self_attention_kernel<64>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st, qkv, ld_qkv, hidden,
-                         key_mask_add, ctx, ld_ctx, L, scale, pdl);
-    }
-    if ((e = set_smem(self_attention_kernel<128>, smem)) != cudaSuccess) return e;
-    return launch_ex(self_attention_kernel<128>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st, qkv, ld_qkv, hidden,
-                     key_mask_add, ctx, ld_ctx, L, scale, pdl);
+    if (head_dim == 64)
+        return f16 ? launch_self<64, true>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st)
+                   : launch_self<64, false>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st);
+    return f16 ? launch_self<128, true>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st)
+               : launch_self<128, false>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st);
+}
+
+template <int D, bool F16>
+static cudaError_t launch_co(const __nv_bfloat16* qkv_img, int ld_img, const __nv_bfloat16* qkv_txt, int ld_txt, int hidden,
+                             const float* img_mask_add, const float* txt_mask_add, __nv_bfloat16* ctx_txt, int ld_ctx_txt,
+                             __nv_bfloat16* ctx_img, int ld_ctx_img, int B, int T, int V, int heads, float scale, size_t smem,
+                             int pdl, cudaStream_t st) {
+    cudaError_t e = set_smem(co_attention_kernel<D, F16>, smem);
+    if (e != cudaSuccess) return e;
+    return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(256), smem, pdl, st, qkv_img, ld_img, qkv_txt, ld_txt,
+                     hidden, img_mask_add, txt_mask_add, ctx_txt, ld_ctx_txt, ctx_img, ld_ctx_img, T, V, scale, pdl);
 }
 
 cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const __nv_bfloat16* qkv_txt, int ld_txt,
                                 int hidden, const float* img_mask_add, const float* txt_mask_add,
                                 __nv_bfloat16* ctx_txt, int ld_ctx_txt, __nv_bfloat16* ctx_img, int ld_ctx_img, int B,
-                                int T, int V, int heads, int head_dim, int pdl, cudaStream_t st) {
+                                int T, int V, int heads, int head_dim, int pdl, int f16, cudaStream_t st) {
     if (T > 32 * kMaxKeyChunks || V > 32 * kMaxKeyChunks || (head_dim != 64 && head_dim != 128) || (ld_img & 7) ||
         (ld_txt & 7) || (hidden & 7) || (ld_ctx_txt & 1) || (ld_ctx_img & 1))
         return cudaErrorInvalidValue;
@@ -212,17 +229,11 @@ cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const 
     const int maxk = T > V ? T : V;
     const size_t smem = 3 * (size_t)(T + V) * stride * 2 + 4 + sizeof(float) * (T + V + nwarps * maxk);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (head_dim == 64) {
-        if ((e = set_smem(co_attention_kernel<64>, smem)) != cudaSuccess) return e;
-        return launch_ex(co_attention_kernel<64>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st, qkv_img, ld_img,
-                         qkv_txt, ld_txt, hidden, img_mask_add, txt_mask_add, ctx_txt, ld_ctx_txt, ctx_img, ld_ctx_img,
-                         T, V, scale, pdl);
-    }
-    if ((e = set_smem(co_attention_kernel<128>, smem)) != cudaSuccess) return e;
-    return launch_ex(co_attention_kernel<128>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st, qkv_img, ld_img,
-                     qkv_txt, ld_txt, hidden, img_mask_add, txt_mask_add, ctx_txt, ld_ctx_txt, ctx_img, ld_ctx_img, T, V,
-                     scale, pdl);
+#define VB_CO(D, F) launch_co<D, F>(qkv_img, ld_img, qkv_txt, ld_txt, hidden, img_mask_add, txt_mask_add, ctx_txt, ld_ctx_txt, \
+                                    ctx_img, ld_ctx_img, B, T, V, heads, scale, smem, pdl, st)
+    if (head_dim == 64) return f16 ? VB_CO(64, true) : VB_CO(64, false);
+    return f16 ? VB_CO(128, true) : VB_CO(128, false);
+#undef VB_CO
 }
 
 }  // namespace vb

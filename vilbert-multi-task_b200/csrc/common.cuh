@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
@@ -126,10 +127,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(const void* smem_ptr)
     return d;
 }
 
-// Instruction descriptor for kind::f16, BF16 x BF16 -> FP32, both operands K-major.
-// [4,6) D fmt (1=F32) | [7,10) A fmt (1=BF16) | [10,13) B fmt | 15/16 A/B major (0=K) | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t m, uint32_t n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// Instruction descriptor for kind::f16, {F16|BF16} x BF16 -> FP32, both operands K-major.
+// [4,6) D fmt (1=F32) | [7,10) A fmt (0=F16, 1=BF16) | [10,13) B fmt | 15/16 A/B major (0=K) | [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(uint32_t m, uint32_t n, bool a_is_f16) {
+    return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
@@ -222,6 +223,32 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+// 16-bit activation format selected at run time (warp-uniform): fp16 (11-bit significand) or bf16 (8-bit).
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+    if constexpr (F16) return pack_h2(lo, hi);
+    else return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t u) {
+    if constexpr (F16) return unpack_h2(u);
+    else return unpack_bf16x2(u);
+}
+__device__ __forceinline__ uint32_t pack16x2_rt(float lo, float hi, int f16) {
+    // fp16 saturates instead of overflowing to inf (activations are LayerNorm-bounded; this is a guard rail)
+    if (f16) return pack_h2(fminf(fmaxf(lo, -65504.0f), 65504.0f), fminf(fmaxf(hi, -65504.0f), 65504.0f));
+    return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint16_t cvt16_rt(float v, int f16) { return static_cast<uint16_t>(pack16x2_rt(v, 0.0f, f16) & 0xffffu); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

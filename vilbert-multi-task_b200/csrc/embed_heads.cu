@@ -17,7 +17,7 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
                   const float* __restrict__ task_tab, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                   float* __restrict__ mask_add, int B, int Tin, int H, int vocab, int max_pos, int n_type, int n_task,
-                  int task_tokens) {
+                  int task_tokens, int f16) {
     const int T = Tin + (task_tokens ? 1 : 0);
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -79,7 +79,7 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
             y.z = (x[k].z - mean) * rstd * g.z + be.z;
             y.w = (x[k].w - mean) * rstd * g.w + be.w;
             of[lane + 32 * k] = y;
-            ob[lane + 32 * k] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+            ob[lane + 32 * k] = make_uint2(pack16x2_rt(y.x, y.y, f16), pack16x2_rt(y.z, y.w, f16));
         }
     }
     if (lane == 0) {
@@ -95,7 +95,7 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
 // one block per (sample, region) row; F % 8 == 0, Kp % 8 == 0, Kp >= F + 8
 __global__ void __launch_bounds__(256)
 image_pack_kernel(const float* __restrict__ feats, const float* __restrict__ loc, const uint8_t* __restrict__ image_mask,
-                  __nv_bfloat16* __restrict__ a_out, float* __restrict__ mask_add, int F, int Kp) {
+                  __nv_bfloat16* __restrict__ a_out, float* __restrict__ mask_add, int F, int Kp, int f16) {
     const int row = blockIdx.x;
     const float4* src = reinterpret_cast<const float4*>(feats + static_cast<size_t>(row) * F);
     uint4* dst = reinterpret_cast<uint4*>(a_out + static_cast<size_t>(row) * Kp);
@@ -103,8 +103,8 @@ image_pack_kernel(const float* __restrict__ feats, const float* __restrict__ loc
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);   // streamed once
         uint4 u;
-        u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
-        u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+        u.x = pack16x2_rt(a.x, a.y, f16); u.y = pack16x2_rt(a.z, a.w, f16);
+        u.z = pack16x2_rt(b.x, b.y, f16); u.w = pack16x2_rt(b.z, b.w, f16);
         dst[i] = u;
     }
     const int tail_vec = (Kp - F) / 8;
@@ -112,9 +112,9 @@ image_pack_kernel(const float* __restrict__ feats, const float* __restrict__ loc
         uint4 u = make_uint4(0, 0, 0, 0);
         if (threadIdx.x == 0) {
             const float* l = loc + static_cast<size_t>(row) * 5;
-            u.x = pack_bf16x2(l[0], l[1]);
-            u.y = pack_bf16x2(l[2], l[3]);
-            u.z = pack_bf16x2(l[4], 0.0f);
+            u.x = pack16x2_rt(l[0], l[1], f16);
+            u.y = pack16x2_rt(l[2], l[3], f16);
+            u.z = pack16x2_rt(l[4], 0.0f, f16);
         }
         dst[nvec + threadIdx.x] = u;
     }
@@ -153,20 +153,20 @@ cudaError_t launch_text_embed(const int64_t* ids, const int64_t* seg, const int6
                               const float* word, const float* pos, const float* type, const float* task_tab,
                               const float* gamma, const float* beta, float eps, float* out_f32,
                               __nv_bfloat16* out_bf16, float* mask_add, int B, int Tin, int H, int vocab, int max_pos,
-                              int n_type, int n_task, int task_tokens, cudaStream_t st) {
+                              int n_type, int n_task, int task_tokens, int f16, cudaStream_t st) {
     if (H % 128 != 0 || H / 128 > kMaxVec) return cudaErrorInvalidValue;
     const int T = Tin + (task_tokens ? 1 : 0);
     const int rows = B * T;
     text_embed_kernel<<<(rows + 3) / 4, 128, 0, st>>>(ids, seg, input_mask, task, word, pos, type, task_tab, gamma, beta,
                                                       eps, out_f32, out_bf16, mask_add, B, Tin, H, vocab, max_pos,
-                                                      n_type, n_task, task_tokens);
+                                                      n_type, n_task, task_tokens, f16);
     return cudaGetLastError();
 }
 
 cudaError_t launch_image_pack(const float* feats, const float* loc, const uint8_t* image_mask, __nv_bfloat16* a_out,
-                              float* mask_add, int rows, int F, int Kp, cudaStream_t st) {
+                              float* mask_add, int rows, int F, int Kp, int f16, cudaStream_t st) {
     if (F % 8 != 0 || Kp % 8 != 0 || Kp < F + 8 || (Kp - F) / 8 > 256) return cudaErrorInvalidValue;
-    image_pack_kernel<<<rows, 256, 0, st>>>(feats, loc, image_mask, a_out, mask_add, F, Kp);
+    image_pack_kernel<<<rows, 256, 0, st>>>(feats, loc, image_mask, a_out, mask_add, F, Kp, f16);
     return cudaGetLastError();
 }
 

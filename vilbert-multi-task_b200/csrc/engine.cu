@@ -269,7 +269,7 @@ EncodeTiledFn get_encode_fn() {
 }
 // bf16 matrix [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle,
 // out-of-bounds elements read as zero.
-CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f16 = false) {
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0)
         fail(VB200_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte-multiple row stride (ld=%lld)", (long long)ld);
     if (box_rows < 1 || box_rows > 256) fail(VB200_ERR_INVALID, "TMA box rows %d out of range", box_rows);
@@ -278,7 +278,7 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+    CUresult r = get_encode_fn()(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(VB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box_rows=%d)",
@@ -599,13 +599,14 @@ struct vb200_engine {
         op.ln = ln != nullptr;
         op.block_n = vb::gemm_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
-        op.ta = make_tmap(A, a_rows, W.ldw, lda, 128);
+        op.ta = make_tmap(A, a_rows, W.ldw, lda, 128, opt.act_fp16 != 0);
         op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.block_n);
         GemmEpilogue& e = op.ep;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
         e.bias = W.bias; e.res = res; e.ld_res = ld_res; e.mul = mul; e.ld_mul = ld_mul;
         e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr; e.eps = cfg.ln_eps;
         e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f; e.act = act; e.pdl = opt.use_pdl;
+        e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
         op.flops = 2.0 * a_rows * W.N * W.K;
         pl.flops += op.flops;
         (void)pl;
@@ -806,12 +807,12 @@ struct vb200_engine {
                 break;
             case Op::SELF_ATTN:
                 CUDA_CHECK(vb::launch_self_attention(op.qkv_a, op.ld_a, op.hidden, op.mask_a, op.ctx_a, op.ld_ctx_a, op.B, op.La,
-                                                     op.heads, op.head_dim, opt.use_pdl, st));
+                                                     op.heads, op.head_dim, opt.use_pdl, opt.act_fp16, st));
                 break;
             case Op::CO_ATTN:
                 CUDA_CHECK(vb::launch_co_attention(op.qkv_a, op.ld_a, op.qkv_b, op.ld_b, op.hidden, op.mask_a, op.mask_b, op.ctx_a,
                                                    op.ld_ctx_a, op.ctx_b, op.ld_ctx_b, op.B, op.La, op.Lb, op.heads, op.head_dim,
-                                                   opt.use_pdl, st));
+                                                   opt.use_pdl, opt.act_fp16, st));
                 break;
             case Op::ROWDOT:
                 CUDA_CHECK(vb::launch_rowdot(op.x, op.ld_x, op.W, op.bias, op.add, op.out, op.ld_out, op.M, op.K, op.n_out, opt.use_pdl, st));
@@ -874,8 +875,8 @@ struct vb200_engine {
             fail(VB200_ERR_INVALID, "vb200_inputs has a NULL required pointer");
         CUDA_CHECK(vb::launch_text_embed(in.question, in.segment_ids, in.input_mask, in.task_tokens, word, pos, type, task,
                                          emb_ln.g, emb_ln.b, c.ln_eps, pl.t_f32[0], pl.t_b16[0], pl.mask_t, pl.B, pl.Tin,
-                                         c.hidden, c.vocab, c.max_pos, c.type_vocab, c.n_task, c.task_tokens, st));
-        CUDA_CHECK(vb::launch_image_pack(in.features, in.spatials, in.image_mask, pl.img_a, pl.mask_v, pl.B * pl.V, c.v_feat, pl.kp, st));
+                                         c.hidden, c.vocab, c.max_pos, c.type_vocab, c.n_task, c.task_tokens, opt.act_fp16, st));
+        CUDA_CHECK(vb::launch_image_pack(in.features, in.spatials, in.image_mask, pl.img_a, pl.mask_v, pl.B * pl.V, c.v_feat, pl.kp, opt.act_fp16, st));
         if (pl.exec) CUDA_CHECK(cudaGraphLaunch(pl.exec, st));
         else run_ops(pl, st);
     }
@@ -947,6 +948,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         o.use_cuda_graph = o.use_cuda_graph >= 0 ? 1 : 0;
         o.strict = o.strict >= 0 ? 1 : 0;
         o.use_pdl = o.use_pdl > 0 ? 1 : 0;
+        o.act_fp16 = o.act_fp16 >= 0 ? 1 : 0;
         Config c = parse_config(config_json);
         {   // audit the state_dict (names, shapes, dtypes, strictness) before touching any device
             vb200_engine audit;
@@ -1060,40 +1062,42 @@ static int op_guard(const std::function<void()>& body) {
 int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t ld_w, const float* bias,
                  const float* residual, int64_t ld_res, const float* gamma, const float* beta, float eps, int32_t act,
                  void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
-                 int32_t block_n, int32_t use_pdl, void* cuda_stream) {
+                 int32_t block_n, int32_t use_pdl, int32_t act_fp16, void* cuda_stream) {
     return op_guard([&] {
         const bool ln = gamma != nullptr;
         int bn = block_n > 0 ? block_n : vb::gemm_pick_block_n(static_cast<int>(N), ln);
         if (bn == 0) fail(VB200_ERR_INVALID, "no tiling for N=%lld with LayerNorm", (long long)N);
-        CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128);
+        CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128, act_fp16 != 0);
         CUtensorMap tb = make_tmap(w_bf16, N, K, ld_w, bn);
         GemmEpilogue e{};
         e.M = (int)M; e.N = (int)N; e.K = (int)K; e.bias = bias; e.res = residual; e.ld_res = (int)ld_res;
         e.gamma = gamma; e.beta = beta; e.eps = eps; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = (int)ld_y_bf16;
         e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.pdl = use_pdl;
+        e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16;
         CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 
 int vb200_self_attention(const void* qkv_bf16, int64_t ld_qkv, int32_t hidden, const float* mask_add, void* ctx_bf16,
-                         int64_t ld_ctx, int32_t B, int32_t L, int32_t heads, int32_t head_dim, void* cuda_stream) {
+                         int64_t ld_ctx, int32_t B, int32_t L, int32_t heads, int32_t head_dim, int32_t act_fp16,
+                         void* cuda_stream) {
     return op_guard([&] {
         CUDA_CHECK(vb::launch_self_attention(static_cast<const bf16*>(qkv_bf16), (int)ld_qkv, hidden, mask_add,
                                              static_cast<bf16*>(ctx_bf16), (int)ld_ctx, B, L, heads, head_dim, 0,
-                                             static_cast<cudaStream_t>(cuda_stream)));
+                                             act_fp16 ? 1 : 0, static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 
 int vb200_co_attention(const void* qkv_img_bf16, int64_t ld_img, const void* qkv_txt_bf16, int64_t ld_txt,
                        int32_t hidden, const float* img_mask_add, const float* txt_mask_add, void* ctx_txt_bf16,
                        int64_t ld_ctx_txt, void* ctx_img_bf16, int64_t ld_ctx_img, int32_t B, int32_t T, int32_t V,
-                       int32_t heads, int32_t head_dim, void* cuda_stream) {
+                       int32_t heads, int32_t head_dim, int32_t act_fp16, void* cuda_stream) {
     return op_guard([&] {
         CUDA_CHECK(vb::launch_co_attention(static_cast<const bf16*>(qkv_img_bf16), (int)ld_img,
                                            static_cast<const bf16*>(qkv_txt_bf16), (int)ld_txt, hidden, img_mask_add,
                                            txt_mask_add, static_cast<bf16*>(ctx_txt_bf16), (int)ld_ctx_txt,
                                            static_cast<bf16*>(ctx_img_bf16), (int)ld_ctx_img, B, T, V, heads, head_dim, 0,
-                                           static_cast<cudaStream_t>(cuda_stream)));
+                                           act_fp16 ? 1 : 0, static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 

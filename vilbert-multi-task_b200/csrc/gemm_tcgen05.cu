@@ -1,6 +1,6 @@
 // K3/K6/K7/K8: every nn.Linear on the ViLBERT hot path as one tcgen05 GEMM with a fused epilogue.
 //
-//   D[M,N] = epilogue( A[M,K] (bf16, row-major)  x  W[N,K]^T (bf16, nn.Linear layout = K-major) )
+//   D[M,N] = epilogue( A[M,K] (fp16 or bf16 activations, row-major)  x  W[N,K]^T (bf16, nn.Linear layout = K-major) )
 //
 // Replaces the cuBLAS SGEMM + separate bias / GELU / residual-add / LayerNorm kernels that the
 // reference's eager PyTorch path launches for BertSelfOutput, BertIntermediate, BertOutput,
@@ -117,7 +117,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N);
+            // A (activations) fp16 or bf16, B (weights) bf16, fp32 accumulate
+            const uint32_t idesc = umma_idesc_f32acc(kBlockM, BLOCK_N, p.a_f16 != 0);
             int s = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -191,15 +192,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint4 u;
-                            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            u.x = pack16x2_rt(v[8 * j + 0], v[8 * j + 1], p.out_f16);
+                            u.y = pack16x2_rt(v[8 * j + 2], v[8 * j + 3], p.out_f16);
+                            u.z = pack16x2_rt(v[8 * j + 4], v[8 * j + 5], p.out_f16);
+                            u.w = pack16x2_rt(v[8 * j + 6], v[8 * j + 7], p.out_f16);
                             reinterpret_cast<uint4*>(op)[j] = u;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (nc + j < p.N) op[j] = __float2bfloat16_rn(v[j]);
+                        for (int j = 0; j < 32; ++j)
+                            if (nc + j < p.N) reinterpret_cast<uint16_t*>(op)[j] = cvt16_rt(v[j], p.out_f16);
                     }
                 }
                 if (p.out_f32 != nullptr) {
@@ -263,10 +265,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint4 u;
-                            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            u.x = pack16x2_rt(v[8 * j + 0], v[8 * j + 1], p.out_f16);
+                            u.y = pack16x2_rt(v[8 * j + 2], v[8 * j + 3], p.out_f16);
+                            u.z = pack16x2_rt(v[8 * j + 4], v[8 * j + 5], p.out_f16);
+                            u.w = pack16x2_rt(v[8 * j + 6], v[8 * j + 7], p.out_f16);
                             reinterpret_cast<uint4*>(op)[j] = u;
                         }
                     }

@@ -23,32 +23,35 @@ struct GemmEpilogue {
     int ld_f32;
     int act;
     int pdl;                      // launched with programmatic stream serialization
+    int a_f16;                    // A operand (activations) is fp16 instead of bf16
+    int out_f16;                  // 16-bit output is fp16 instead of bf16
 };
 
 int gemm_pick_block_n(int N, bool ln);
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep, int block_n,
                         bool ln, cudaStream_t st);
 
+// 16-bit activation buffers are typed __nv_bfloat16* throughout; `f16` says the bits are IEEE fp16 instead.
 // K4: softmax(Q K^T / sqrt(d) + mask) V per (sample, head); qkv row = [Q | K | V], each `hidden` wide.
 cudaError_t launch_self_attention(const __nv_bfloat16* qkv, int ld_qkv, int hidden, const float* key_mask_add,
                                   __nv_bfloat16* ctx, int ld_ctx, int B, int L, int heads, int head_dim, int pdl,
-                                  cudaStream_t st);
+                                  int f16, cudaStream_t st);
 // K5: both co-attention directions in one kernel.  qkv_img rows = [Q1|K1|V1], qkv_txt rows = [Q2|K2|V2].
 //   ctx_txt[b,t] = softmax(Q2 K1^T / sqrt(d) + img_mask) V1      ctx_img[b,v] = softmax(Q1 K2^T / sqrt(d) + txt_mask) V2
 cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const __nv_bfloat16* qkv_txt, int ld_txt,
                                 int hidden, const float* img_mask_add, const float* txt_mask_add,
                                 __nv_bfloat16* ctx_txt, int ld_ctx_txt, __nv_bfloat16* ctx_img, int ld_ctx_img, int B,
-                                int T, int V, int heads, int head_dim, int pdl, cudaStream_t st);
+                                int T, int V, int heads, int head_dim, int pdl, int f16, cudaStream_t st);
 
 // K2: word + position + token-type gather, task-token row at index 1, LayerNorm; also builds the additive text mask.
 cudaError_t launch_text_embed(const int64_t* ids, const int64_t* seg, const int64_t* input_mask, const int64_t* task,
                               const float* word, const float* pos, const float* type, const float* task_tab,
                               const float* gamma, const float* beta, float eps, float* out_f32,
                               __nv_bfloat16* out_bf16, float* mask_add, int B, int Tin, int H, int vocab, int max_pos,
-                              int n_type, int n_task, int task_tokens, cudaStream_t st);
+                              int n_type, int n_task, int task_tokens, int f16, cudaStream_t st);
 // K1 (input half): fp32 region features + 5-d boxes -> bf16 GEMM operand [B*V, Kp] = [feat | loc | 0], additive image mask.
 cudaError_t launch_image_pack(const float* feats, const float* loc, const uint8_t* image_mask, __nv_bfloat16* a_out,
-                              float* mask_add, int rows, int F, int Kp, cudaStream_t st);
+                              float* mask_add, int rows, int F, int Kp, int f16, cudaStream_t st);
 // K8 (narrow heads): out[m, j] = dot(x[m, :K], W[j, :K]) + b[j] + (add ? add[m] : 0), j < n_out <= 4.
 cudaError_t launch_rowdot(const float* x, int ld_x, const float* W, const float* b, const float* add, float* out,
                           int ld_out, int M, int K, int n_out, int pdl, cudaStream_t st);
