@@ -109,9 +109,10 @@ typedef struct {
     int32_t use_cuda_graph;        /* default on: each (B,Tin,V,select) plan is captured once and replayed */
     int32_t use_pdl;               /* default off: programmatic dependent launch between consecutive kernels */
     int32_t strict;                /* default on: unexpected checkpoint keys are an error */
-    int32_t act_fp16;              /* default on: 16-bit activations are IEEE fp16 (11-bit significand, LayerNorm-bounded
-                                      values, saturating converts); -1: bf16 activations.  Weights are bf16 either way,
-                                      accumulation / residual stream / LayerNorm / softmax / logits are fp32. */
+    int32_t act_fp16;              /* 16-bit format of the tensor-core operands (weights AND activations; tcgen05 kind::f16
+                                      needs matching A/B formats).  default on: IEEE fp16 (11-bit significand; activations
+                                      are LayerNorm-bounded, converts saturate); -1: bf16.  Accumulation, residual stream,
+                                      LayerNorm, softmax and logits are fp32 either way. */
 } vb200_options;
 
 int vb200_abi_version(void);
@@ -139,12 +140,14 @@ int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_r
 int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
 
 /* ---- Kernel-level entry points (device pointers), used by the parity tests and the roofline bench.  ---- */
-/* y = epilogue(x[M,K] (16-bit) . w[N,K]^T (bf16)); act: 0 none, 1 GELU(erf), 2 ReLU; LayerNorm applied when gamma != NULL.
- * act_fp16 != 0: x and the 16-bit output y are fp16, else bf16 (parameter names keep the historical _bf16 suffix). */
+/* y = epilogue(x[M,K] (16-bit) . w[N,K]^T (16-bit)); act: 0 none, 1 GELU(erf), 2 ReLU; LayerNorm applied when gamma != NULL.
+ * act_fp16 != 0: x, w and the 16-bit output y are fp16, else bf16 (parameter names keep the historical _bf16 suffix).
+ * variant 0: persistent kernel (gemm_persistent.cu, what the engine uses); 1: one-tile-per-CTA kernel (gemm_tcgen05.cu).
+ * timing: NULL, or a device buffer of 8 int64 per CTA that receives clock64() phase stamps (profiling aid, variant 0). */
 int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t ld_w, const float* bias,
                  const float* residual, int64_t ld_res, const float* gamma, const float* beta, float eps, int32_t act,
                  void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
-                 int32_t block_n, int32_t use_pdl, int32_t act_fp16, void* cuda_stream);
+                 int32_t block_n, int32_t use_pdl, int32_t act_fp16, int32_t variant, long long* timing, void* cuda_stream);
 /* ctx = softmax(Q K^T / sqrt(d) + mask) V, qkv rows = [Q | K | V] (bf16), mask_add fp32 [B, L]. */
 int vb200_self_attention(const void* qkv_bf16, int64_t ld_qkv, int32_t hidden, const float* mask_add, void* ctx_bf16,
                          int64_t ld_ctx, int32_t B, int32_t L, int32_t heads, int32_t head_dim, int32_t act_fp16,

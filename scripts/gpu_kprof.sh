@@ -1,11 +1,16 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 600 python scripts/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1
-echo "kb exit $?" > gpurun_out/status.txt
-# full ncu capture of three representative kernels (one launch each, after warm-up)
-for k in text_ffn_out_ln text_ffn_in_gelu self_attn_text; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16|attention' -s 6 -c 1 \
-     -o gpurun_out/prof_$k -f python scripts/kernel_bench.py --only $k --reps 3 --sets 1 > gpurun_out/ncu_$k.log 2>&1
-  echo "ncu $k exit $?" >> gpurun_out/status.txt
-done
-cat gpurun_out/kernel_bench.log; cat gpurun_out/status.txt
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; rm -f gpurun_out/parity.jsonl gpurun_out/status.txt
+timeout 900 python -m pytest tests/test_gpu_ops.py -m gpu -q -x --timeout=240 -p no:cacheprovider > gpurun_out/pytest_ops.log 2>&1
+echo "ops exit $?" >> gpurun_out/status.txt
+timeout 600 python scripts/kernel_bench.py --stamps > gpurun_out/kernel_bench.log 2>&1
+echo "kb exit $?" >> gpurun_out/status.txt
+timeout 600 python scripts/kernel_bench.py --variant 1 > gpurun_out/kernel_bench_v1.log 2>&1
+timeout 600 python scripts/kernel_bench.py --batch 512 --reps 20 > gpurun_out/kernel_bench_b512.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_model.py -m gpu -q --timeout=900 -p no:cacheprovider > gpurun_out/pytest_model.log 2>&1
+echo "model exit $?" >> gpurun_out/status.txt
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1
+VB200_GEMM=v1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_v1.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --batch 512 > gpurun_out/bench_b512.log 2>&1
+tail -5 gpurun_out/pytest_ops.log; cat gpurun_out/kernel_bench.log; echo V1; cat gpurun_out/kernel_bench_v1.log; echo B512; cat gpurun_out/kernel_bench_b512.log; tail -15 gpurun_out/pytest_model.log
+for f in plain v1 b512; do tail -1 gpurun_out/bench_$f.log | cut -c1-200; done; cat gpurun_out/status.txt

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--act", default="fp16")
     ap.add_argument("--sets", type=int, default=4, help="operand sets cycled through per kernel")
+    ap.add_argument("--variant", type=int, default=0, help="0 persistent kernel, 1 one-tile-per-CTA kernel")
+    ap.add_argument("--stamps", action="store_true", help="print clock64 phase stamps of the persistent kernel")
     a = ap.parse_args()
     lib = L.load()
     B, T, V = a.batch, 31, 36
@@ -51,7 +53,7 @@ def main():
         sets = []
         for _ in range(a.sets):
             x = torch.randn(M, K, generator=g, device="cuda").to(act)
-            w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+            w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(act)
             b = torch.randn(N, generator=g, device="cuda")
             r = torch.randn(M, N, generator=g, device="cuda") if ln else None
             ga = torch.ones(N, device="cuda") if ln else None
@@ -64,7 +66,7 @@ def main():
         def run(i):
             x, w, b, r, ga, be, yb, yf, ldf = sets[i % a.sets]
             rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
-                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, C.c_void_p(st))
+                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, None, C.c_void_p(st))
             L.check(rc, None)
         for i in range(5):
             run(i)
@@ -79,6 +81,19 @@ def main():
         fl = 2.0 * M * N * K
         res.append(dict(kernel=name, M=M, N=N, K=K, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
         print(json.dumps(res[-1]), flush=True)
+        if a.stamps and a.variant == 0:
+            tb = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
+            x, w, b, r, ga, be, yb, yf, ldf = sets[0]
+            rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
+                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, 0, ptr(tb), C.c_void_p(st))
+            L.check(rc, None)
+            torch.cuda.synchronize()
+            t = tb.view(-1, 8).cpu()
+            t = t[t[:, 0] != 0]
+            d = (t - t[:, :1]).double()
+            names = ["entry", "setup", "first_kblock", "mma_issued", "acc_ready", "epi_pass1", "ln_exchange", "epi_done"]
+            print("   stamps (SM cycles since CTA entry, median over %d CTAs): " % len(t) +
+                  ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names) if (t[:, i] != 0).any()), flush=True)
 
     attn = [("self_attn_text", 12, 64, T), ("self_attn_img", 8, 128, V)]
     for name, heads, d, Lq in attn:

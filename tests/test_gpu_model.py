@@ -3,9 +3,9 @@ fp32 CPU oracle on identical seeded inputs.  `-m gpu` only.
 
 Tolerances (BASELINE.json north_star: "within 1e-3 fp32 / 1e-2 bf16 per logit"):
 
-* TOL = 1e-2 per logit against the fp32 oracle -- met by the DEFAULT engine mode (bf16 weights x fp16 activations,
-  fp32 accumulation / residual stream / LayerNorm / softmax).
-* The pure-bf16-activation mode (act_dtype="bf16") cannot meet 1e-2 against fp32: rounding the ~150 GEMM operands of
+* TOL = 1e-2 per logit against the fp32 oracle -- met by the DEFAULT engine mode (fp16 tensor-core operands,
+  fp32 accumulation / residual stream / LayerNorm / softmax; same tcgen05 kind::f16 rate as bf16).
+* The bf16-operand mode (compute_dtype="bf16") cannot meet 1e-2 against fp32: rounding the ~150 GEMM operands of
   this network to an 8-bit significand moves the VQA logits (std 0.91) by up to ~1.9e-2 in *exact* arithmetic --
   the oracle itself shows it when its activations are rounded to bf16 at the same points
   (oracle.emulate_activation_rounding; tests/test_oracle.py pins that number on CPU).  That mode is therefore checked
@@ -41,7 +41,7 @@ def _engine(oracle, **kw):
 
 @pytest.fixture(scope="module")
 def tiny_engines(tiny_oracle):
-    e = {k: _engine(tiny_oracle, act_dtype=k) for k in DT}
+    e = {k: _engine(tiny_oracle, compute_dtype=k) for k in DT}
     yield e
     for m in e.values():
         m.close()
@@ -49,7 +49,7 @@ def tiny_engines(tiny_oracle):
 
 @pytest.fixture(scope="module")
 def full_engines(full_oracle):
-    e = {k: _engine(full_oracle, act_dtype=k) for k in DT}
+    e = {k: _engine(full_oracle, compute_dtype=k) for k in DT}
     yield e
     for m in e.values():
         m.close()

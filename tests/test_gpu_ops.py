@@ -18,9 +18,20 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+VARIANT = 0     # 0 = persistent kernel (engine default), 1 = one-tile-per-CTA kernel; set per test via the fixture
+
+
+@pytest.fixture(params=[0, 1], ids=["persistent", "v1"])
+def variant(request):
+    global VARIANT
+    VARIANT = request.param
+    yield request.param
+    VARIANT = 0
+
+
 def run_linear(x, w, bias=None, res=None, gamma=None, beta=None, act=0, block_n=0, want_bf16=True, want_f32=True,
                ld_f32=None, pdl=0):
-    """x: fp16 or bf16 activations (the 16-bit output has the same format); w: bf16 weights."""
+    """x, w: both fp16 or both bf16 (tcgen05 kind::f16 needs matching operand formats); same format for the 16-bit output."""
     L, lib = _lib()
     M, K = x.shape
     N = w.shape[0]
@@ -32,7 +43,7 @@ def run_linear(x, w, bias=None, res=None, gamma=None, beta=None, act=0, block_n=
     stream = torch.cuda.current_stream().cuda_stream
     rc = lib.vb200_linear(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(res),
                           res.stride(0) if res is not None else 0, _ptr(gamma), _ptr(beta), 1e-12, act,
-                          _ptr(yb), N, _ptr(yf), ldf, M, N, K, block_n, pdl, f16, C.c_void_p(stream))
+                          _ptr(yb), N, _ptr(yf), ldf, M, N, K, block_n, pdl, f16, VARIANT, None, C.c_void_p(stream))
     L.check(rc, None)
     torch.cuda.synchronize()
     return yb, (yf[:, :N] if yf is not None else None)
@@ -61,7 +72,7 @@ ACT = [torch.float16, torch.bfloat16]
 def _mk(M, N, K, seed=0, act=torch.bfloat16):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn(M, K, generator=g, device="cuda").to(act)
-    w = (torch.randn(N, K, generator=g, device="cuda") * (1.0 / math.sqrt(K))).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") * (1.0 / math.sqrt(K))).to(act)
     b = torch.randn(N, generator=g, device="cuda") * 0.1
     return x, w, b, g
 
@@ -76,9 +87,10 @@ def _mk(M, N, K, seed=0, act=torch.bfloat16):
     (1984, 3072, 768, 256),     # wide tile
     (77, 64, 128, 64),          # narrow tile
     (64, 3129, 2048, 128),      # VQA logits: ragged N, M < tile
+    (15872, 3072, 768, 128),    # B=512 text FFN-in: 2976 tiles, ~10 per persistent CTA
 ])
 @pytest.mark.parametrize("act_dt", ACT)
-def test_linear_bias(M, N, K, block_n, act_dt, parity_log):
+def test_linear_bias(M, N, K, block_n, act_dt, variant, parity_log):
     x, w, b, _ = _mk(M, N, K, act=act_dt)
     ld = (N + 3) // 4 * 4
     yb, yf = run_linear(x, w, b, block_n=block_n, ld_f32=ld)
@@ -93,7 +105,7 @@ def test_linear_bias(M, N, K, block_n, act_dt, parity_log):
 
 @pytest.mark.parametrize("act_dt", ACT)
 @pytest.mark.parametrize("act", [1, 2])
-def test_linear_act(act, act_dt, parity_log):
+def test_linear_act(act, act_dt, variant, parity_log):
     x, w, b, _ = _mk(300, 1024, 512, seed=1, act=act_dt)
     _, yf = run_linear(x, w, b, act=act)
     ref = ref_linear(x, w, b, act=act)
@@ -109,9 +121,11 @@ def test_linear_act(act, act_dt, parity_log):
     (1984, 768, 3072, 0),       # text FFN-out
     (2304, 1024, 2112, 0),      # image embedding: cluster of 8, K with zero tail
     (64, 2048, 1024, 1),        # SimpleClassifier: GELU then LayerNorm over 2048 = 256 x 8
+    (5000, 1024, 512, 0),       # 40 M tiles: persistent clusters loop (accumulator + partial double-buffering)
+    (16000, 768, 256, 1),       # 125 M tiles over <= 24 clusters of 6
 ])
 @pytest.mark.parametrize("act_dt", ACT)
-def test_linear_residual_layernorm(M, N, K, act, act_dt, parity_log):
+def test_linear_residual_layernorm(M, N, K, act, act_dt, variant, parity_log):
     x, w, b, g = _mk(M, N, K, seed=2, act=act_dt)
     res = torch.randn(M, N, generator=g, device="cuda")
     gamma = 1.0 + 0.1 * torch.randn(N, generator=g, device="cuda")
@@ -136,7 +150,7 @@ def test_linear_inplace_residual():
     ref = ref_linear(x, w, b, res=res, gamma=gamma, beta=beta)
     buf = res.clone()
     rc = lib.vb200_linear(_ptr(x), K, _ptr(w), K, _ptr(b), _ptr(buf), N, _ptr(gamma), _ptr(beta), 1e-12, 0,
-                          None, 0, _ptr(buf), N, M, N, K, 0, 0, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                          None, 0, _ptr(buf), N, M, N, K, 0, 0, 0, 0, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     L.check(rc, None)
     torch.cuda.synchronize()
     assert (buf - ref).abs().max().item() < 2e-3

@@ -90,7 +90,7 @@ def load():
     lib.vb200_plan_info.argtypes = [vp, i32, i32, i32, u32, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb200_model_dim.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     lib.vb200_linear.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, f32, i32, vp, i64, vp, i64,
-                                 i64, i64, i64, i32, i32, i32, vp]
+                                 i64, i64, i64, i32, i32, i32, i32, vp, vp]
     lib.vb200_self_attention.argtypes = [vp, i64, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp]
     lib.vb200_co_attention.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     for name in EXPORTS:

@@ -4,233 +4,301 @@
 // BertSelfAttention / BertImageSelfAttention, and the 4 bmm + 2 softmax of BertBiAttention
 // ([UPSTREAM] vilbert/vilbert.py; anchor /root/reference/worker.py:286-289).
 //
-// Sequences are tiny (T <= 129, V <= 101) and attention is < 1 % of the FLOPs, so the win is
-// fusion and launch count, not tensor throughput: one CTA owns one (sample, head), stages
-// Q/K/V once in shared memory as bf16 (rows padded by one bank so row-strided reads are
-// conflict-free), one warp owns one query row: scores with keys across lanes, a warp-shuffle
-// softmax in fp32, then P.V with channels across lanes.  The co-attention kernel stages the six
-// operand tiles of a (sample, head) once and produces BOTH directions (text-query x image-key and
-// image-query x text-key) from them.
+// Sequences are tiny (T <= 129, V <= 101) and attention is < 1 % of the FLOPs, so the goals are fusion, launch
+// count and instruction count -- not tcgen05 throughput (a 128-row UMMA tile would be 75 % padding at T = 31).
+// One CTA owns one (sample, head): Q/K/V head slices are staged once in shared memory (16-bit, rows padded by
+// 16 B so ldmatrix is conflict-free); each warp owns 16 query rows and runs a register-resident flash-attention
+// pass over the keys in blocks of 64: S = Q K^T on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32
+// accumulate), additive key mask, online softmax with quad shuffles in fp32, P V again on mma.sync.
+// The co-attention kernel stages the six operand tiles of a (sample, head) once and produces BOTH directions
+// (text-query x image-key -> text context, image-query x text-key -> image context) from them.
 #include "kernels.h"
 
 namespace vb {
 
-constexpr int kMaxKeyChunks = 8;   // keys <= 256
+constexpr int kKeyBlock = 64;             // keys per online-softmax block
+constexpr float kLog2e = 1.4426950408889634f;
 
 template <int D>
-struct AttnSmem {
-    static constexpr int kStride = D + 2;   // bf16 elements per padded row: (D/2 + 1) words -> odd -> conflict-free
-    static size_t tile_bytes(int rows) { return static_cast<size_t>(rows) * kStride * 2; }
+struct AttnTile {
+    static constexpr int kStride = D + 8;                 // 16-bit elements per padded row (row = D*2 + 16 bytes)
+    static size_t bytes(int rows) { return static_cast<size_t>(rows) * kStride * 2; }
 };
 
-// rows x D bf16 tile: global (row stride ld, 16-byte aligned rows) -> padded shared
+__host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
+
+// rows x D 16-bit tile: global (row stride ld elements, 16-byte aligned) -> padded shared with cp.async (every 16-byte
+// copy of every tile is in flight before anyone waits); rows [rows, rows_pad) are zero-filled (src-size 0).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 template <int D>
-__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int rows, int ld) {
-    constexpr int kVecPerRow = D / 8;
-    constexpr int kStride = AttnSmem<D>::kStride;
-    for (int i = threadIdx.x; i < rows * kVecPerRow; i += blockDim.x) {
-        const int r = i / kVecPerRow, c = i % kVecPerRow;
-        const uint4 u = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld + c * 8);
-        uint32_t* d = reinterpret_cast<uint32_t*>(dst + r * kStride + c * 8);
-        d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+__device__ __forceinline__ void load_tile(uint16_t* dst, const uint16_t* src, int rows, int rows_pad, int ld) {
+    constexpr int kVec = D / 8;
+    constexpr int kStride = AttnTile<D>::kStride;
+    for (int i = threadIdx.x; i < rows_pad * kVec; i += blockDim.x) {
+        const int r = i / kVec, c = i % kVec;
+        const bool ok = r < rows;
+        cp_async16(dst + r * kStride + c * 8, src + (ok ? static_cast<size_t>(r) * ld + c * 8 : 0), ok);
     }
 }
 
-// One warp per query row.  Qs/Ks/Vs: padded bf16 tiles.  mask_add[j] additive key mask (fp32).
-// out: bf16 global, row stride ld_out, already offset to this head's first column.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+template <bool F16>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (F16) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+}
+
+// One warp: 16 query rows [r0, r0+16) of Qs against nk keys (Ks/Vs zero-padded to a multiple of 16 rows).
+// mask_l2[j] = additive key mask * log2(e).  out: 16-bit global, already offset to this head's first column.
 template <int D, bool F16>
-__device__ __forceinline__ void attend_rows(const __nv_bfloat16* Qs, const __nv_bfloat16* Ks, const __nv_bfloat16* Vs,
-                                            int nq, int nk, const float* mask_add, float scale, float* p_warp,
-                                            __nv_bfloat16* out, int ld_out, int warp, int nwarps, int lane) {
-    constexpr int kStride = AttnSmem<D>::kStride;
-    for (int i = warp; i < nq; i += nwarps) {
-        const uint32_t* qrow = reinterpret_cast<const uint32_t*>(Qs + i * kStride);
-        float s[kMaxKeyChunks];
-        float mx = -INFINITY;
+__device__ __forceinline__ void attend_tile(const uint16_t* Qs, const uint16_t* Ks, const uint16_t* Vs, int r0, int nq,
+                                            int nk, const float* mask_l2, float scale_l2, uint16_t* out, int ld_out,
+                                            int lane) {
+    constexpr int kStride = AttnTile<D>::kStride;
+    constexpr int kKSteps = D / 16;         // k-steps of Q K^T
+    constexpr int kONTiles = D / 8;         // 8-wide output column tiles
+    const int g = lane >> 2, tq = lane & 3;  // row within 8, column pair within 8
+
+    uint32_t qa[kKSteps][4];
 #pragma unroll
-        for (int jj = 0; jj < kMaxKeyChunks; ++jj) {
-            s[jj] = -INFINITY;
-            if (jj * 32 < nk) {
-                const int j = jj * 32 + lane;
-                if (j < nk) {
-                    const uint32_t* krow = reinterpret_cast<const uint32_t*>(Ks + j * kStride);
-                    float acc = 0.0f;
-#pragma unroll 8
-                    for (int k2 = 0; k2 < D / 2; ++k2) {
-                        const float2 q = unpack16x2<F16>(qrow[k2]);
-                        const float2 k = unpack16x2<F16>(krow[k2]);
-                        acc = fmaf(q.x, k.x, acc);
-                        acc = fmaf(q.y, k.y, acc);
-                    }
-                    s[jj] = acc * scale + mask_add[j];
+    for (int ks = 0; ks < kKSteps; ++ks)
+        ldsm_x4(qa[ks], Qs + (r0 + (lane & 15)) * kStride + ks * 16 + (lane >> 4) * 8);
+
+    float o[kONTiles][4];
+#pragma unroll
+    for (int i = 0; i < kONTiles; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;   // running max / sum for rows g and g+8
+
+    const int nk_pad = pad16(nk);
+    for (int kb = 0; kb < nk_pad; kb += kKeyBlock) {
+        const int nkeys = min(kKeyBlock, nk_pad - kb);            // multiple of 16
+        float s[kKeyBlock / 8][4];
+        // ---- S = Q K^T for this key block
+#pragma unroll
+        for (int nt = 0; nt < kKeyBlock / 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+            if (nt * 8 < nkeys) {
+#pragma unroll
+                for (int ks2 = 0; ks2 < kKSteps / 2; ++ks2) {
+                    uint32_t kf[4];   // keys nt*8..+8: k-cols [ks2*32, +8), [+8,+16), [+16,+24), [+24,+32)
+                    ldsm_x4(kf, Ks + (kb + nt * 8 + (lane & 7)) * kStride + ks2 * 32 + (lane >> 3) * 8);
+                    mma16816<F16>(s[nt], qa[2 * ks2], kf[0], kf[1]);
+                    mma16816<F16>(s[nt], qa[2 * ks2 + 1], kf[2], kf[3]);
                 }
-                mx = fmaxf(mx, s[jj]);
             }
         }
-        mx = warp_max(mx);
-        float sum = 0.0f;
+        // ---- scale + mask (log2 domain), block row max
+        float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-        for (int jj = 0; jj < kMaxKeyChunks; ++jj) {
-            if (jj * 32 < nk) {
-                const int j = jj * 32 + lane;
-                const float e = (j < nk) ? __expf(s[jj] - mx) : 0.0f;
-                s[jj] = e;
-                sum += e;
+        for (int nt = 0; nt < kKeyBlock / 8; ++nt) {
+            if (nt * 8 < nkeys) {
+                const int j = kb + nt * 8 + tq * 2;
+                const float ma = j < nk ? mask_l2[j] : -INFINITY;
+                const float mb = j + 1 < nk ? mask_l2[j + 1] : -INFINITY;
+                s[nt][0] = fmaf(s[nt][0], scale_l2, ma); s[nt][1] = fmaf(s[nt][1], scale_l2, mb);
+                s[nt][2] = fmaf(s[nt][2], scale_l2, ma); s[nt][3] = fmaf(s[nt][3], scale_l2, mb);
+                bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+                bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
             }
         }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);   // finite: every block holds >= 1 real key
+        const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);   // exp2f(-inf) = 0 on the first block
+        m0 = nm0; m1 = nm1;
+        float bs0 = 0.0f, bs1 = 0.0f;
 #pragma unroll
-        for (int jj = 0; jj < kMaxKeyChunks; ++jj) {
-            if (jj * 32 < nk) {
-                const int j = jj * 32 + lane;
-                if (j < nk) p_warp[j] = s[jj] * inv;
+        for (int nt = 0; nt < kKeyBlock / 8; ++nt) {
+            if (nt * 8 < nkeys) {
+                s[nt][0] = exp2f(s[nt][0] - nm0); s[nt][1] = exp2f(s[nt][1] - nm0);
+                s[nt][2] = exp2f(s[nt][2] - nm1); s[nt][3] = exp2f(s[nt][3] - nm1);
+                bs0 += s[nt][0] + s[nt][1];
+                bs1 += s[nt][2] + s[nt][3];
             }
         }
-        __syncwarp();
-        // O[i, :] = sum_j p[j] V[j, :]; lane owns channels {2*lane + 64*cc, +1}
-        float2 acc[D / 64];
+        l0 = l0 * c0 + bs0;                  // per-lane partial sums; reduced over the quad at the end
+        l1 = l1 * c1 + bs1;
 #pragma unroll
-        for (int cc = 0; cc < D / 64; ++cc) acc[cc] = make_float2(0.0f, 0.0f);
-        for (int j = 0; j < nk; ++j) {
-            const float pj = p_warp[j];
-            const uint32_t* vrow = reinterpret_cast<const uint32_t*>(Vs + j * kStride);
+        for (int i = 0; i < kONTiles; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+        // ---- O += P V   (P: C fragments of two adjacent key tiles form one A fragment)
 #pragma unroll
-            for (int cc = 0; cc < D / 64; ++cc) {
-                const float2 v = unpack16x2<F16>(vrow[lane + 32 * cc]);
-                acc[cc].x = fmaf(pj, v.x, acc[cc].x);
-                acc[cc].y = fmaf(pj, v.y, acc[cc].y);
+        for (int kk = 0; kk < kKeyBlock / 16; ++kk) {
+            if (kk * 16 < nkeys) {
+                uint32_t pa[4];
+                pa[0] = pack16x2<F16>(s[2 * kk][0], s[2 * kk][1]);
+                pa[1] = pack16x2<F16>(s[2 * kk][2], s[2 * kk][3]);
+                pa[2] = pack16x2<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+                pa[3] = pack16x2<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+                for (int nt2 = 0; nt2 < kONTiles / 2; ++nt2) {
+                    uint32_t vf[4];   // V[keys kk*16..+16][cols nt2*16..+16] transposed on load
+                    ldsm_x4_trans(vf, Vs + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kStride + nt2 * 16 + (lane >> 4) * 8);
+                    mma16816<F16>(o[2 * nt2], pa, vf[0], vf[1]);
+                    mma16816<F16>(o[2 * nt2 + 1], pa, vf[2], vf[3]);
+                }
             }
         }
-        uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<size_t>(i) * ld_out);
-#pragma unroll
-        for (int cc = 0; cc < D / 64; ++cc) orow[lane + 32 * cc] = pack16x2<F16>(acc[cc].x, acc[cc].y);
-        __syncwarp();   // p_warp reused by the next row
     }
-}
-
-template <int D, bool F16>
-__global__ void __launch_bounds__(128)
-self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int hidden,
-                      const float* __restrict__ key_mask_add, __nv_bfloat16* __restrict__ ctx, int ld_ctx, int L,
-                      float scale, int pdl) {
-    extern __shared__ __align__(16) uint8_t smem_attn[];
-    constexpr int kStride = AttnSmem<D>::kStride;
-    const int h = blockIdx.x, b = blockIdx.y;
-    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-    __nv_bfloat16* Ks = Qs + L * kStride;
-    __nv_bfloat16* Vs = Ks + L * kStride;
-    float* mask_s = reinterpret_cast<float*>(Vs + L * kStride + (L * kStride & 1));
-    float* p_all = mask_s + L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-
-    if (pdl) { pdl_wait(); pdl_launch_dependents(); }
-
-    const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * L * ld_qkv + h * D;
-    load_tile<D>(Qs, base, L, ld_qkv);
-    load_tile<D>(Ks, base + hidden, L, ld_qkv);
-    load_tile<D>(Vs, base + 2 * hidden, L, ld_qkv);
-    for (int j = threadIdx.x; j < L; j += blockDim.x) mask_s[j] = key_mask_add[b * L + j];
-    __syncthreads();
-    attend_rows<D, F16>(Qs, Ks, Vs, L, L, mask_s, scale, p_all + warp * L,
-                   ctx + static_cast<size_t>(b) * L * ld_ctx + h * D, ld_ctx, warp, nwarps, lane);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+#pragma unroll
+    for (int nt = 0; nt < kONTiles; ++nt) {
+        const int col = nt * 8 + tq * 2;
+        if (row0 < nq) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row0) * ld_out + col) = pack16x2<F16>(o[nt][0] * i0, o[nt][1] * i0);
+        if (row1 < nq) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row1) * ld_out + col) = pack16x2<F16>(o[nt][2] * i1, o[nt][3] * i1);
+    }
 }
 
 template <int D, bool F16>
 __global__ void __launch_bounds__(256)
-co_attention_kernel(const __nv_bfloat16* __restrict__ qkv_img, int ld_img, const __nv_bfloat16* __restrict__ qkv_txt,
-                    int ld_txt, int hidden, const float* __restrict__ img_mask_add,
-                    const float* __restrict__ txt_mask_add, __nv_bfloat16* __restrict__ ctx_txt, int ld_ctx_txt,
-                    __nv_bfloat16* __restrict__ ctx_img, int ld_ctx_img, int T, int V, float scale, int pdl) {
+self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, const float* __restrict__ key_mask_add,
+                      uint16_t* __restrict__ ctx, int ld_ctx, int L, float scale_l2, int pdl) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
-    constexpr int kStride = AttnSmem<D>::kStride;
+    constexpr int kStride = AttnTile<D>::kStride;
     const int h = blockIdx.x, b = blockIdx.y;
-    __nv_bfloat16* Q1 = reinterpret_cast<__nv_bfloat16*>(smem_attn);   // image side: V rows
-    __nv_bfloat16* K1 = Q1 + V * kStride;
-    __nv_bfloat16* V1 = K1 + V * kStride;
-    __nv_bfloat16* Q2 = V1 + V * kStride;                               // text side: T rows
-    __nv_bfloat16* K2 = Q2 + T * kStride;
-    __nv_bfloat16* V2 = K2 + T * kStride;
-    const int tot = 3 * (T + V) * kStride;
-    float* mask_img = reinterpret_cast<float*>(Q1 + tot + (tot & 1));
-    float* mask_txt = mask_img + V;
-    float* p_all = mask_txt + T;
+    const int Lp = pad16(L);
+    uint16_t* Qs = reinterpret_cast<uint16_t*>(smem_attn);
+    uint16_t* Ks = Qs + Lp * kStride;
+    uint16_t* Vs = Ks + Lp * kStride;
+    float* mask_s = reinterpret_cast<float*>(Vs + Lp * kStride);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int maxk = T > V ? T : V;
 
     if (pdl) { pdl_wait(); pdl_launch_dependents(); }
 
-    const __nv_bfloat16* bi = qkv_img + static_cast<size_t>(b) * V * ld_img + h * D;
-    const __nv_bfloat16* bt = qkv_txt + static_cast<size_t>(b) * T * ld_txt + h * D;
-    load_tile<D>(Q1, bi, V, ld_img);
-    load_tile<D>(K1, bi + hidden, V, ld_img);
-    load_tile<D>(V1, bi + 2 * hidden, V, ld_img);
-    load_tile<D>(Q2, bt, T, ld_txt);
-    load_tile<D>(K2, bt + hidden, T, ld_txt);
-    load_tile<D>(V2, bt + 2 * hidden, T, ld_txt);
-    for (int j = threadIdx.x; j < V; j += blockDim.x) mask_img[j] = img_mask_add[b * V + j];
-    for (int j = threadIdx.x; j < T; j += blockDim.x) mask_txt[j] = txt_mask_add[b * T + j];
+    const uint16_t* base = qkv + static_cast<size_t>(b) * L * ld_qkv + h * D;
+    load_tile<D>(Qs, base, L, Lp, ld_qkv);
+    load_tile<D>(Ks, base + hidden, L, Lp, ld_qkv);
+    load_tile<D>(Vs, base + 2 * hidden, L, Lp, ld_qkv);
+    for (int j = threadIdx.x; j < L; j += blockDim.x) mask_s[j] = key_mask_add[b * L + j] * kLog2e;
+    cp_async_wait_all();
     __syncthreads();
-    // text queries over image keys/values -> context for the text stream
-    attend_rows<D, F16>(Q2, K1, V1, T, V, mask_img, scale, p_all + warp * maxk,
-                   ctx_txt + static_cast<size_t>(b) * T * ld_ctx_txt + h * D, ld_ctx_txt, warp, nwarps, lane);
-    // image queries over text keys/values -> context for the image stream
-    attend_rows<D, F16>(Q1, K2, V2, V, T, mask_txt, scale, p_all + warp * maxk,
-                   ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D, ld_ctx_img, warp, nwarps, lane);
+    uint16_t* outp = ctx + static_cast<size_t>(b) * L * ld_ctx + h * D;
+    for (int t = warp; t * 16 < L; t += nwarps)
+        attend_tile<D, F16>(Qs, Ks, Vs, t * 16, L, L, mask_s, scale_l2, outp, ld_ctx, lane);
+}
+
+template <int D, bool F16>
+__global__ void __launch_bounds__(256)
+co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint16_t* __restrict__ qkv_txt, int ld_txt,
+                    int hidden, const float* __restrict__ img_mask_add, const float* __restrict__ txt_mask_add,
+                    uint16_t* __restrict__ ctx_txt, int ld_ctx_txt, uint16_t* __restrict__ ctx_img, int ld_ctx_img, int T,
+                    int V, float scale_l2, int pdl) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    constexpr int kStride = AttnTile<D>::kStride;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int Tp = pad16(T), Vp = pad16(V);
+    uint16_t* Q1 = reinterpret_cast<uint16_t*>(smem_attn);   // image side: V rows
+    uint16_t* K1 = Q1 + Vp * kStride;
+    uint16_t* V1 = K1 + Vp * kStride;
+    uint16_t* Q2 = V1 + Vp * kStride;                        // text side: T rows
+    uint16_t* K2 = Q2 + Tp * kStride;
+    uint16_t* V2 = K2 + Tp * kStride;
+    float* mask_img = reinterpret_cast<float*>(V2 + Tp * kStride);
+    float* mask_txt = mask_img + V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+    if (pdl) { pdl_wait(); pdl_launch_dependents(); }
+
+    const uint16_t* bi = qkv_img + static_cast<size_t>(b) * V * ld_img + h * D;
+    const uint16_t* bt = qkv_txt + static_cast<size_t>(b) * T * ld_txt + h * D;
+    load_tile<D>(Q1, bi, V, Vp, ld_img);
+    load_tile<D>(K1, bi + hidden, V, Vp, ld_img);
+    load_tile<D>(V1, bi + 2 * hidden, V, Vp, ld_img);
+    load_tile<D>(Q2, bt, T, Tp, ld_txt);
+    load_tile<D>(K2, bt + hidden, T, Tp, ld_txt);
+    load_tile<D>(V2, bt + 2 * hidden, T, Tp, ld_txt);
+    for (int j = threadIdx.x; j < V; j += blockDim.x) mask_img[j] = img_mask_add[b * V + j] * kLog2e;
+    for (int j = threadIdx.x; j < T; j += blockDim.x) mask_txt[j] = txt_mask_add[b * T + j] * kLog2e;
+    cp_async_wait_all();
+    __syncthreads();
+    uint16_t* out_t = ctx_txt + static_cast<size_t>(b) * T * ld_ctx_txt + h * D;
+    uint16_t* out_v = ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D;
+    const int tt = Tp / 16, tv = Vp / 16;
+    for (int t = warp; t < tt + tv; t += nwarps) {
+        if (t < tt)   // text queries over image keys/values -> context for the text stream
+            attend_tile<D, F16>(Q2, K1, V1, t * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane);
+        else          // image queries over text keys/values -> context for the image stream
+            attend_tile<D, F16>(Q1, K2, V2, (t - tt) * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane);
+    }
 }
 
 template <int D, bool F16>
 static cudaError_t launch_self(const __nv_bfloat16* qkv, int ld_qkv, int hidden, const float* key_mask_add,
-                               __nv_bfloat16* ctx, int ld_ctx, int B, int L, int heads, float scale, size_t smem, int pdl,
-                               cudaStream_t st) {
+                               __nv_bfloat16* ctx, int ld_ctx, int B, int L, int heads, int pdl, cudaStream_t st) {
+    const int Lp = pad16(L);
+    const size_t smem = 3 * AttnTile<D>::bytes(Lp) + sizeof(float) * L;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = set_smem(self_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(128), smem, pdl, st, qkv, ld_qkv, hidden,
-                     key_mask_add, ctx, ld_ctx, L, scale, pdl);
+    const int nwarps = min(8, Lp / 16);
+    const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
+    return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
+                     reinterpret_cast<const uint16_t*>(qkv), ld_qkv, hidden, key_mask_add, reinterpret_cast<uint16_t*>(ctx),
+                     ld_ctx, L, scale_l2, pdl);
 }
 
 cudaError_t launch_self_attention(const __nv_bfloat16* qkv, int ld_qkv, int hidden, const float* key_mask_add,
                                   __nv_bfloat16* ctx, int ld_ctx, int B, int L, int heads, int head_dim, int pdl,
                                   int f16, cudaStream_t st) {
-    if (L > 32 * kMaxKeyChunks || (head_dim != 64 && head_dim != 128) || (ld_qkv & 7) || (ld_ctx & 1) || (hidden & 7))
+    if (L < 1 || (head_dim != 64 && head_dim != 128) || (ld_qkv & 7) || (ld_ctx & 1) || (hidden & 7))
         return cudaErrorInvalidValue;
-    const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-    const int nwarps = 4;
-    const size_t stride = head_dim + 2;
-    const size_t smem = 3 * L * stride * 2 + 4 + sizeof(float) * (L + nwarps * L);
     if (head_dim == 64)
-        return f16 ? launch_self<64, true>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st)
-                   : launch_self<64, false>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st);
-    return f16 ? launch_self<128, true>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st)
-               : launch_self<128, false>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, scale, smem, pdl, st);
+        return f16 ? launch_self<64, true>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, pdl, st)
+                   : launch_self<64, false>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, pdl, st);
+    return f16 ? launch_self<128, true>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, pdl, st)
+               : launch_self<128, false>(qkv, ld_qkv, hidden, key_mask_add, ctx, ld_ctx, B, L, heads, pdl, st);
 }
 
 template <int D, bool F16>
 static cudaError_t launch_co(const __nv_bfloat16* qkv_img, int ld_img, const __nv_bfloat16* qkv_txt, int ld_txt, int hidden,
                              const float* img_mask_add, const float* txt_mask_add, __nv_bfloat16* ctx_txt, int ld_ctx_txt,
-                             __nv_bfloat16* ctx_img, int ld_ctx_img, int B, int T, int V, int heads, float scale, size_t smem,
-                             int pdl, cudaStream_t st) {
+                             __nv_bfloat16* ctx_img, int ld_ctx_img, int B, int T, int V, int heads, int pdl,
+                             cudaStream_t st) {
+    const int Tp = pad16(T), Vp = pad16(V);
+    const size_t smem = 3 * AttnTile<D>::bytes(Tp + Vp) + sizeof(float) * (T + V);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;     // T + V too long for one CTA's shared memory
     cudaError_t e = set_smem(co_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(256), smem, pdl, st, qkv_img, ld_img, qkv_txt, ld_txt,
-                     hidden, img_mask_add, txt_mask_add, ctx_txt, ld_ctx_txt, ctx_img, ld_ctx_img, T, V, scale, pdl);
+    const int nwarps = min(8, (Tp + Vp) / 16);
+    const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
+    return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
+                     reinterpret_cast<const uint16_t*>(qkv_img), ld_img, reinterpret_cast<const uint16_t*>(qkv_txt), ld_txt,
+                     hidden, img_mask_add, txt_mask_add, reinterpret_cast<uint16_t*>(ctx_txt), ld_ctx_txt,
+                     reinterpret_cast<uint16_t*>(ctx_img), ld_ctx_img, T, V, scale_l2, pdl);
 }
 
 cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const __nv_bfloat16* qkv_txt, int ld_txt,
                                 int hidden, const float* img_mask_add, const float* txt_mask_add,
                                 __nv_bfloat16* ctx_txt, int ld_ctx_txt, __nv_bfloat16* ctx_img, int ld_ctx_img, int B,
                                 int T, int V, int heads, int head_dim, int pdl, int f16, cudaStream_t st) {
-    if (T > 32 * kMaxKeyChunks || V > 32 * kMaxKeyChunks || (head_dim != 64 && head_dim != 128) || (ld_img & 7) ||
-        (ld_txt & 7) || (hidden & 7) || (ld_ctx_txt & 1) || (ld_ctx_img & 1))
+    if (T < 1 || V < 1 || (head_dim != 64 && head_dim != 128) || (ld_img & 7) || (ld_txt & 7) || (hidden & 7) ||
+        (ld_ctx_txt & 1) || (ld_ctx_img & 1))
         return cudaErrorInvalidValue;
-    const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-    const int nwarps = 8;
-    const size_t stride = head_dim + 2;
-    const int maxk = T > V ? T : V;
-    const size_t smem = 3 * (size_t)(T + V) * stride * 2 + 4 + sizeof(float) * (T + V + nwarps * maxk);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
 #define VB_CO(D, F) launch_co<D, F>(qkv_img, ld_img, qkv_txt, ld_txt, hidden, img_mask_add, txt_mask_add, ctx_txt, ld_ctx_txt, \
-                                    ctx_img, ld_ctx_img, B, T, V, heads, scale, smem, pdl, st)
+                                    ctx_img, ld_ctx_img, B, T, V, heads, pdl, st)
     if (head_dim == 64) return f16 ? VB_CO(64, true) : VB_CO(64, false);
     return f16 ? VB_CO(128, true) : VB_CO(128, false);
 #undef VB_CO

@@ -127,10 +127,11 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(const void* smem_ptr)
     return d;
 }
 
-// Instruction descriptor for kind::f16, {F16|BF16} x BF16 -> FP32, both operands K-major.
+// Instruction descriptor for kind::f16: F16 x F16 or BF16 x BF16 -> FP32, both operands K-major.
+// (Mixing F16 activations with BF16 weights is encodable but traps as an illegal instruction on sm_100a -- measured.)
 // [4,6) D fmt (1=F32) | [7,10) A fmt (0=F16, 1=BF16) | [10,13) B fmt | 15/16 A/B major (0=K) | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_f32acc(uint32_t m, uint32_t n, bool a_is_f16) {
-    return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(uint32_t m, uint32_t n, bool is_f16) {
+    return (1u << 4) | ((is_f16 ? 0u : 1u) << 7) | ((is_f16 ? 0u : 1u) << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
@@ -203,8 +204,10 @@ __device__ __forceinline__ void cluster_sync_all() {  // every thread of every C
 __device__ __forceinline__ float dsmem_ld_f32(const float* local_smem_ptr, uint32_t rank) {
     uint32_t remote;
     float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+    // volatile (not hoisted above the cluster barrier, which clobbers memory) but no memory clobber of its own, so the
+    // loads from all peers are issued back to back instead of one round trip at a time
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
     return v;
 }
 
@@ -213,7 +216,22 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ math
-__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26): branch-free, 2 MUFU + ~10 FMA-class instructions per value.
+// The libdevice erff costs several times more (two range-dependent paths, both executed by a divergent warp), and the
+// GELU epilogue evaluates it 16K times per 128x128 tile on only four warps.
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float e = exp2f(-1.4426950408889634f * ax * ax);
+    return copysignf(fmaf(-poly, e, 1.0f), x);
+}
+// GELU, erf form: x * 0.5 * (1 + erf(x / sqrt(2)))   ([UPSTREAM] vilbert.py `gelu`)
+__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

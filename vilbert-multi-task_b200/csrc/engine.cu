@@ -205,6 +205,13 @@ struct Arena {   // owns every device allocation of an engine / plan
     ~Arena() { for (void* p : ptrs) cudaFree(p); }
 };
 
+inline uint16_t f32_to_f16_bits(float f) {          // IEEE half, round to nearest even, saturating to +-65504
+    const __half h = __float2half_rn(f);            // host-callable conversion from cuda_fp16.h
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    if ((b & 0x7fffu) == 0x7c00u) b = static_cast<uint16_t>((b & 0x8000u) | 0x7bffu);
+    return b;
+}
 inline uint16_t f32_to_bf16_bits(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -346,6 +353,7 @@ struct vb200_engine {
     vb200_options opt{};
     int num_labels = 0, gqa_labels = 0;
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
+    bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     Arena weights;
     std::string last_error;
     // embeddings
@@ -425,6 +433,7 @@ struct vb200_engine {
             if (extra_k) { need(extra_k_prefix + ".weight", 2, n_each, extra_k); need(extra_k_prefix + ".bias", 1, n_each); }
             return L;
         }
+        const bool f16 = opt.act_fp16 != 0;     // weights are stored in the same 16-bit format as the activations
         std::vector<uint16_t> h(static_cast<size_t>(L.N) * L.ldw, 0);
         std::vector<float> hb(L.N, 0.0f);
         for (size_t pi = 0; pi < prefixes.size(); ++pi) {
@@ -434,9 +443,10 @@ struct vb200_engine {
                 uint16_t* dst = &h[(pi * n_each + n) * L.ldw];
                 if (w.dtype == VB200_F32) {
                     const float* src = static_cast<const float*>(w.data) + n * k;
-                    for (int64_t j = 0; j < k; ++j) dst[j] = f32_to_bf16_bits(src[j]);
+                    if (f16) for (int64_t j = 0; j < k; ++j) dst[j] = f32_to_f16_bits(src[j]);
+                    else for (int64_t j = 0; j < k; ++j) dst[j] = f32_to_bf16_bits(src[j]);
                 } else {
-                    for (int64_t j = 0; j < k; ++j) dst[j] = f32_to_bf16_bits(w.at(n * k + j));
+                    for (int64_t j = 0; j < k; ++j) dst[j] = cvt16(w.at(n * k + j));
                 }
                 hb[pi * n_each + n] = b.at(n);
             }
@@ -445,7 +455,7 @@ struct vb200_engine {
             HostTensor& w = need(extra_k_prefix + ".weight", 2, n_each, extra_k);
             HostTensor& b = need(extra_k_prefix + ".bias", 1, n_each);
             for (int64_t n = 0; n < n_each; ++n) {
-                for (int64_t j = 0; j < extra_k; ++j) h[n * L.ldw + k + j] = f32_to_bf16_bits(w.at(n * extra_k + j));
+                for (int64_t j = 0; j < extra_k; ++j) h[n * L.ldw + k + j] = cvt16(w.at(n * extra_k + j));
                 hb[n] += b.at(n);
             }
         }
@@ -454,6 +464,7 @@ struct vb200_engine {
         L.bias = upload_f32(hb);
         return L;
     }
+    uint16_t cvt16(float f) const { return opt.act_fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); }
     LinearW load_linear1(const std::string& prefix, int64_t n, int64_t k) { return load_linear({prefix}, n, k); }
     RowW load_row(const std::string& prefix, int n_out, int k) {
         RowW r; r.n_out = n_out; r.K = k;
@@ -560,7 +571,7 @@ struct vb200_engine {
             HostTensor& w = need("bert.embeddings.word_embeddings.weight", 2, c.vocab, c.hidden);
             if (!dry) {
                 std::vector<uint16_t> h(static_cast<size_t>(c.vocab) * c.hidden);
-                for (size_t i = 0; i < h.size(); ++i) h[i] = f32_to_bf16_bits(w.at(i));
+                for (size_t i = 0; i < h.size(); ++i) h[i] = cvt16(w.at(i));
                 word_b16 = weights.alloc_n<bf16>(h.size());
                 CUDA_CHECK(cudaMemcpy(word_b16, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
             }
@@ -597,10 +608,10 @@ struct vb200_engine {
         op.kind = Op::GEMM;
         op.stream = stream;
         op.ln = ln != nullptr;
-        op.block_n = vb::gemm_pick_block_n(W.N, op.ln);
+        op.block_n = gemm_v1 ? vb::gemm_pick_block_n(W.N, op.ln) : vb::gemm_p_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
         op.ta = make_tmap(A, a_rows, W.ldw, lda, 128, opt.act_fp16 != 0);
-        op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.block_n);
+        op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.block_n, opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
         e.bias = W.bias; e.res = res; e.ld_res = ld_res; e.mul = mul; e.ld_mul = ld_mul;
@@ -803,7 +814,8 @@ struct vb200_engine {
     void launch_op(const Op& op, cudaStream_t st) {
         switch (op.kind) {
             case Op::GEMM:
-                CUDA_CHECK(vb::launch_gemm(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
+                if (gemm_v1) CUDA_CHECK(vb::launch_gemm(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
+                else CUDA_CHECK(vb::launch_gemm_persistent(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
                 break;
             case Op::SELF_ATTN:
                 CUDA_CHECK(vb::launch_self_attention(op.qkv_a, op.ld_a, op.hidden, op.mask_a, op.ctx_a, op.ld_ctx_a, op.B, op.La,
@@ -959,6 +971,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng = new vb200_engine();
         eng->cfg = c;
         eng->opt = o;
+        if (const char* v = getenv("VB200_GEMM")) eng->gemm_v1 = (strcmp(v, "v1") == 0);
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
@@ -1062,19 +1075,22 @@ static int op_guard(const std::function<void()>& body) {
 int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t ld_w, const float* bias,
                  const float* residual, int64_t ld_res, const float* gamma, const float* beta, float eps, int32_t act,
                  void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
-                 int32_t block_n, int32_t use_pdl, int32_t act_fp16, void* cuda_stream) {
+                 int32_t block_n, int32_t use_pdl, int32_t act_fp16, int32_t variant, long long* timing, void* cuda_stream) {
     return op_guard([&] {
         const bool ln = gamma != nullptr;
-        int bn = block_n > 0 ? block_n : vb::gemm_pick_block_n(static_cast<int>(N), ln);
+        int bn = block_n > 0 ? block_n
+                             : (variant == 1 ? vb::gemm_pick_block_n(static_cast<int>(N), ln)
+                                             : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
         if (bn == 0) fail(VB200_ERR_INVALID, "no tiling for N=%lld with LayerNorm", (long long)N);
         CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128, act_fp16 != 0);
-        CUtensorMap tb = make_tmap(w_bf16, N, K, ld_w, bn);
+        CUtensorMap tb = make_tmap(w_bf16, N, K, ld_w, bn, act_fp16 != 0);
         GemmEpilogue e{};
         e.M = (int)M; e.N = (int)N; e.K = (int)K; e.bias = bias; e.res = residual; e.ld_res = (int)ld_res;
         e.gamma = gamma; e.beta = beta; e.eps = eps; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = (int)ld_y_bf16;
         e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.pdl = use_pdl;
-        e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16;
-        CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
+        e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16; e.timing = timing;
+        if (variant == 1) CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
+        else CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 

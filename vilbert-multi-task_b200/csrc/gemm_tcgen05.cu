@@ -1,6 +1,7 @@
 // K3/K6/K7/K8: every nn.Linear on the ViLBERT hot path as one tcgen05 GEMM with a fused epilogue.
 //
-//   D[M,N] = epilogue( A[M,K] (fp16 or bf16 activations, row-major)  x  W[N,K]^T (bf16, nn.Linear layout = K-major) )
+//   D[M,N] = epilogue( A[M,K] (16-bit activations, row-major)  x  W[N,K]^T (16-bit, nn.Linear layout = K-major) )
+//   16-bit = fp16 (default) or bf16 for BOTH operands (tcgen05 kind::f16 needs matching A/B formats), fp32 accumulate.
 //
 // Replaces the cuBLAS SGEMM + separate bias / GELU / residual-add / LayerNorm kernels that the
 // reference's eager PyTorch path launches for BertSelfOutput, BertIntermediate, BertOutput,
@@ -31,14 +32,16 @@ struct GemmCfg {
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 192 ? 5 : (BLOCK_N >= 96 ? 6 : 8));
+    // Ring depth sized for TWO resident CTAs per SM (<= ~110 KB each): one CTA's prologue / epilogue overlaps the other's
+    // main loop, and the text- and image-stream kernels of the captured graph can share an SM.
+    static constexpr int kStages = BLOCK_N >= 256 ? 2 : (BLOCK_N >= 192 ? 2 : (BLOCK_N >= 128 ? 3 : (BLOCK_N >= 96 ? 3 : 4)));
     // ring | bias,gamma,beta (3*BLOCK_N f32) | part1,part2 (2*128 f32) | barriers | tmem ptr
     static constexpr int kSmemAux = 3 * BLOCK_N * 4 + 2 * kBlockM * 4 + (2 * kStages + 1) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux + 1024;  // +1024 for manual alignment
 };
 
 template <int BLOCK_N, bool LN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmEpilogue p) {
     using Cfg = GemmCfg<BLOCK_N>;
@@ -117,7 +120,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            // A (activations) fp16 or bf16, B (weights) bf16, fp32 accumulate
+            // A (activations) and B (weights) both fp16 or both bf16, fp32 accumulate
             const uint32_t idesc = umma_idesc_f32acc(kBlockM, BLOCK_N, p.a_f16 != 0);
             int s = 0;
             uint32_t phase = 0;

@@ -23,13 +23,20 @@ struct GemmEpilogue {
     int ld_f32;
     int act;
     int pdl;                      // launched with programmatic stream serialization
-    int a_f16;                    // A operand (activations) is fp16 instead of bf16
+    int a_f16;                    // both GEMM operands (activations A, weights W) are fp16 instead of bf16
     int out_f16;                  // 16-bit output is fp16 instead of bf16
+    long long* timing;            // optional (profiling): 8 clock64 stamps per CTA, see gemm_persistent.cu; null in production
 };
 
 int gemm_pick_block_n(int N, bool ln);
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep, int block_n,
                         bool ln, cudaStream_t st);
+
+// v2: persistent CTAs / clusters, TMEM double-buffered accumulators, single-exchange LayerNorm (gemm_persistent.cu)
+int gemm_p_pick_block_n(int N, bool ln);
+int gemm_p_max_clusters(int block_n, int cluster);
+cudaError_t launch_gemm_persistent(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep,
+                                   int block_n, bool ln, cudaStream_t st);
 
 // 16-bit activation buffers are typed __nv_bfloat16* throughout; `f16` says the bits are IEEE fp16 instead.
 // K4: softmax(Q K^T / sqrt(d) + mask) V per (sample, head); qkv row = [Q | K | V], each `hidden` wide.
