@@ -82,16 +82,17 @@ def main():
         res.append(dict(kernel=name, M=M, N=N, K=K, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
         print(json.dumps(res[-1]), flush=True)
         if a.stamps and a.variant == 0:
-            tb = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
+            tb = torch.zeros(16 * 4096, dtype=torch.int64, device="cuda")
             x, w, b, r, ga, be, yb, yf, ldf = sets[0]
             rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
                                   ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, 0, ptr(tb), C.c_void_p(st))
             L.check(rc, None)
             torch.cuda.synchronize()
-            t = tb.view(-1, 8).cpu()
+            t = tb.view(-1, 16).cpu()
             t = t[t[:, 0] != 0]
             d = (t - t[:, :1]).double()
-            names = ["entry", "setup", "first_kblock", "mma_issued", "acc_ready", "epi_pass1", "ln_exchange", "epi_done"]
+            names = ["entry", "setup", "first_kblock", "mma_issued", "acc_ready", "epi_pass1", "ln_exchange", "epi_done",
+                     "c0_ld", "c0_res", "c0_math", "c0_store", "c1_ld", "c1_res", "c1_math", "c1_store"]
             print("   stamps (SM cycles since CTA entry, median over %d CTAs): " % len(t) +
                   ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names) if (t[:, i] != 0).any()), flush=True)
 

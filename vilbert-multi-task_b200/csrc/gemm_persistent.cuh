@@ -1,0 +1,527 @@
+// Persistent, warp-specialised tcgen05 GEMM (v2 of K3/K6/K7/K8): same math and epilogues as gemm_tcgen05.cu, but
+//   * each CTA (each CLUSTER for the LayerNorm variant) loops over output tiles, so barrier init, TMEM allocation,
+//     descriptor prefetch and the TMA/L2 latency of the first k-block are paid once per kernel, not once per tile;
+//   * the TMA producer runs ahead across tile boundaries (the shared-memory ring never drains);
+//   * the fp32 accumulator is double-buffered in TMEM (2 x BLOCK_N columns): the epilogue of tile i overlaps the MMAs
+//     of tile i+1, and the accumulator is handed back as soon as it has been read into registers;
+//   * epilogue code is specialised OUTSIDE the per-element loops (activation, 16-bit format) -- measured: per-element
+//     run-time branches made a bias-only epilogue cost 11 k cycles per 128x128 tile, 4x the MMA time;
+//   * the fp32 residual of the next 32-column chunk is prefetched while the current chunk is processed, and the first
+//     chunk's residual is requested before the accumulator is even ready;
+//   * LayerNorm (8 epilogue warps, x kept in registers, TMEM read once) exchanges ONE (mean, M2) pair per row, column
+//     half and CTA through distributed shared memory (Chan's parallel variance), synchronised by cluster-scope
+//     mbarriers that only the epilogue warps touch -- producer and MMA warps are never stalled by the normalisation.
+//
+//   D[M,N] = epilogue( A[M,K] (16-bit, row-major)  x  W[N,K]^T (16-bit, nn.Linear layout = K-major) ), fp32 accumulate.
+#pragma once
+#include <algorithm>
+#include "kernels.h"
+
+namespace vb {
+
+namespace pgemm {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+
+template <int BLOCK_N, bool LN>
+struct PCfg {
+    static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+    static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+    static constexpr int kNumChunks = BLOCK_N / 32;
+    // Ring depth.  Measured L2->smem latency under load is ~1600 cycles and one 128x128x64 k-block is 256 MMA cycles, so
+    // an SM needs ~6 stages in flight to be MMA-bound.  Plain tiles: 3 stages x 2 CTAs per SM (the second CTA also lets a
+    // kernel of the other ViLBERT stream share the SM).  LayerNorm tiles run one CTA per SM (clusters, 8 epilogue warps
+    // with the row slice in registers) and take the whole ring themselves.
+    static constexpr int kEpiWarps = LN ? 8 : 4;
+    static constexpr int kEpiThreads = 32 * kEpiWarps;
+    static constexpr int kThreads = 64 + kEpiThreads;            // warp 0 TMA, warp 1 MMA (+TMEM alloc), then epilogue
+    static constexpr int kMinBlocks = (LN || BLOCK_N >= 192) ? 1 : 2;
+    static constexpr int kFit = 200 * 1024 / kStageBytes;
+    static constexpr int kStages = kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit);
+    static constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    // LN: chunks per epilogue thread (two column halves per TMEM lane quarter)
+    static constexpr int kCPT = (kNumChunks + 1) / 2;
+    // ring | bias[2][BLOCK_N] gamma beta (4*BLOCK_N f32) | part[2 bufs][2 halves][128] float2 | barriers | tmem ptr
+    static constexpr int kNumBars = 2 * kStages + 4 + 2;
+    static constexpr int kSmemAux = 4 * BLOCK_N * 4 + 4 * kBlockM * 8 + kNumBars * 8 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux + 1024;
+};
+
+// ---- cluster-scope mbarrier helpers (LayerNorm exchange)
+__device__ __forceinline__ uint32_t mapa_u32(const void* local_smem_ptr, uint32_t rank) {
+    uint32_t remote;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > VB_SPIN_LIMIT) {
+            printf("vb: cluster mbarrier timeout block(%d,%d) thread %d\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ float2 dsmem_ld_f32x2(uint32_t cluster_addr) {
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
+    return v;
+}
+template <int kThreadsInBar>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreadsInBar) : "memory"); }
+
+// ---- TMEM load split into issue / wait so a chunk's load overlaps the previous chunk's math and stores
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    __syncwarp();
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- straight-line per-chunk epilogue pieces (all flags resolved outside the element loops)
+template <int ACT>
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias_s) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = reinterpret_cast<const float4*>(bias_s)[j4];     // smem broadcast, 16-byte reads
+        float x0 = v[4 * j4 + 0] + b.x, x1 = v[4 * j4 + 1] + b.y, x2 = v[4 * j4 + 2] + b.z, x3 = v[4 * j4 + 3] + b.w;
+        if (ACT == kActGelu) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+        if (ACT == kActRelu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); x2 = fmaxf(x2, 0.0f); x3 = fmaxf(x3, 0.0f); }
+        v[4 * j4 + 0] = x0; v[4 * j4 + 1] = x1; v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
+    }
+}
+template <bool F16>
+__device__ __forceinline__ void store16x32(__nv_bfloat16* op, const float (&v)[32]) {   // 64 contiguous bytes, 16-byte aligned
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = F16 ? pack16x2_rt(v[8 * j + 0], v[8 * j + 1], 1) : pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = F16 ? pack16x2_rt(v[8 * j + 2], v[8 * j + 3], 1) : pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = F16 ? pack16x2_rt(v[8 * j + 4], v[8 * j + 5], 1) : pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = F16 ? pack16x2_rt(v[8 * j + 6], v[8 * j + 7], 1) : pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        reinterpret_cast<uint4*>(op)[j] = u;
+    }
+}
+__device__ __forceinline__ void store_f32x32(float* op, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// general (ragged N / unaligned ld) path
+__device__ __noinline__ static void store_chunk_slow(const GemmEpilogue& p, int m, int nc, const float* v) {
+    if (p.out_bf16 != nullptr) {
+        uint16_t* op = reinterpret_cast<uint16_t*>(p.out_bf16) + static_cast<size_t>(m) * p.ld_bf16 + nc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (nc + j < p.N) op[j] = cvt16_rt(v[j], p.out_f16);
+    }
+    if (p.out_f32 != nullptr) {
+        float* op = p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + nc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (nc + j < p.N) op[j] = v[j];
+    }
+}
+template <bool F16>
+__device__ __forceinline__ void store_chunk(const GemmEpilogue& p, int m, int nc, bool fast, const float (&v)[32]) {
+    if (fast) {
+        if (p.out_bf16 != nullptr) store16x32<F16>(p.out_bf16 + static_cast<size_t>(m) * p.ld_bf16 + nc, v);
+        if (p.out_f32 != nullptr) store_f32x32(p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + nc, v);
+    } else {
+        float tmp[32];                       // only this (ragged N / odd stride) path touches local memory
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+        store_chunk_slow(p, m, nc, tmp);
+    }
+}
+// residual: 32 fp32 of row m starting at column nc -> 8 float4 (plain loads: res may alias out_f32)
+__device__ __forceinline__ void res_load(const GemmEpilogue& p, int m, int nc, bool fast, float4 (&r)[8]) {
+    const float* rp = p.res + static_cast<size_t>(m) * p.ld_res + nc;
+    if (fast) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = reinterpret_cast<const float4*>(rp)[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            r[j].x = nc + 4 * j + 0 < p.N ? rp[4 * j + 0] : 0.0f;
+            r[j].y = nc + 4 * j + 1 < p.N ? rp[4 * j + 1] : 0.0f;
+            r[j].z = nc + 4 * j + 2 < p.N ? rp[4 * j + 2] : 0.0f;
+            r[j].w = nc + 4 * j + 3 < p.N ? rp[4 * j + 3] : 0.0f;
+        }
+    }
+}
+__device__ __forceinline__ void res_add(float (&v)[32], const float4 (&r)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[4 * j] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w; }
+}
+
+template <int BLOCK_N, bool LN, int ACT, bool F16>
+__global__ void __launch_bounds__(PCfg<BLOCK_N, LN>::kThreads, PCfg<BLOCK_N, LN>::kMinBlocks)
+gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const GemmEpilogue p, const int num_m_tiles, const int num_n_tiles) {
+    using Cfg = PCfg<BLOCK_N, LN>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kNC = Cfg::kNumChunks;
+    constexpr int kEpiThreads = Cfg::kEpiThreads;
+    static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "epilogue works in 32-column chunks");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    float* s_bias = reinterpret_cast<float*>(ring + kStages * Cfg::kStageBytes);   // [2][BLOCK_N]
+    float* s_gamma = s_bias + 2 * BLOCK_N;
+    float* s_beta = s_gamma + BLOCK_N;
+    float2* s_part = reinterpret_cast<float2*>(s_beta + BLOCK_N);                   // [2 bufs][2 halves][128] (mean, M2)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + 4 * kBlockM);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint64_t* ln_bar = tmem_empty_bar + 2;             // [2] cluster exchange, alternating per tile so that arrivals
+                                                       //     for tile i+1 can never be counted into tile i's phase
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ln_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+    // profiling stamps (first tile of each CTA): 0 entry, 1 setup done, 2 first k-block landed, 3 last MMA issued,
+    // 4 accumulator ready, 5 accumulator read + local statistics done, 6 LayerNorm exchange done, 7 epilogue done
+    long long* stamps = p.timing ? p.timing + 16 * (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    if (stamps && threadIdx.x == 0) stamps[0] = clock64();
+
+    // ---- tile assignment.  Non-LN: CTA b takes tiles b, b+grid, ... with the N index fastest (CTAs that run together
+    // share an A row-panel in L2).  LN: gridDim.x = cluster size = num_n_tiles, blockIdx.y = cluster id; cluster c takes
+    // M tiles c, c + gridDim.y, ... and the CTA's rank in the cluster is its (fixed) N tile.
+    const int total_tiles = LN ? num_m_tiles : num_m_tiles * num_n_tiles;
+    const int first_tile = LN ? static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.x);
+    const int tile_stride = LN ? static_cast<int>(gridDim.y) : static_cast<int>(gridDim.x);
+    const uint32_t cluster_size = LN ? cluster_nctarank() : 1u;
+    const uint32_t my_rank = LN ? cluster_ctarank() : 0u;
+
+    // ---------------------------------------------------------------- one-time setup
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], kEpiThreads);
+            mbar_init(&ln_bar[a], LN ? cluster_size * Cfg::kEpiWarps : 1u);   // one arrival per epilogue warp in the cluster
+        }
+        mbar_fence_init();
+    } else if (warp == 1) {
+        tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+    } else if (LN && warp >= 2) {
+        const int n0 = static_cast<int>(my_rank) * BLOCK_N;
+        for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) {
+            s_bias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+            s_gamma[i] = p.gamma[n0 + i];
+            s_beta[i] = p.beta[n0 + i];
+        }
+    }
+    tc_fence_before();
+    if (LN) cluster_sync_all(); else __syncthreads();   // LN: peers' barriers must be initialised before remote arrives
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (stamps && threadIdx.x == 0) stamps[1] = clock64();
+
+    if (p.pdl) {
+        pdl_wait();
+        pdl_launch_dependents();
+    }
+
+    if (warp == 0) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+                const int m0 = (LN ? tile : tile / num_n_tiles) * kBlockM;
+                const int n0 = (LN ? static_cast<int>(my_rank) : tile % num_n_tiles) * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], phase ^ 1u);
+                    uint8_t* sa = ring + s * Cfg::kStageBytes;
+                    uint8_t* sb = sa + Cfg::kStageBytesA;
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                    tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+                    tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0);
+                    if (++s == kStages) { s = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f32acc(kBlockM, BLOCK_N, F16);
+            int s = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+                const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[s], phase);
+                    tc_fence_after();
+                    if (stamps && it == 0 && kb == 0) stamps[2] = clock64();
+                    uint8_t* sa = ring + s * Cfg::kStageBytes;
+                    const uint64_t da = umma_desc_kmajor_sw128(sa);
+                    const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kStages) { s = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full_bar[acc]);
+                if (stamps && it == 0) stamps[3] = clock64();
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================================================ epilogue warps
+        const int ew = warp - 2;                      // 0..kEpiWarps-1
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = LN ? (ew >> 2) : 0;          // LN: column half of the tile
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;
+        const bool st_fast = (p.out_bf16 == nullptr || (p.ld_bf16 & 7) == 0) && (p.out_f32 == nullptr || (p.ld_f32 & 3) == 0);
+        uint32_t it = 0;
+        for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const int m0 = (LN ? tile : tile / num_n_tiles) * kBlockM;
+            const int n0 = (LN ? static_cast<int>(my_rank) : tile % num_n_tiles) * BLOCK_N;
+            const int m = m0 + row;
+            const bool m_ok = m < p.M;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            const bool stamp = stamps && it == 0 && et == 0;
+
+            if constexpr (!LN) {
+                // ------------------------------------------------ plain epilogue: 4 warps, chunk-pipelined
+                float* bias_t = s_bias + acc * BLOCK_N;
+                // per-tile bias slice, double-buffered by accumulator parity; the named barrier also orders this tile's
+                // writes after every epilogue warp has finished the tile that last used the buffer
+                for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_t[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
+                epi_bar_sync<kEpiThreads>();
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+                if (stamp) stamps[4] = clock64();
+                float va[32], vb[32];
+                tmem_ld32_issue(taddr, va);
+#pragma unroll
+                for (int c = 0; c < kNC; ++c) {
+                    float (&v)[32] = (c & 1) ? vb : va;
+                    float (&vn)[32] = (c & 1) ? va : vb;
+                    const int nc = n0 + c * 32;
+                    tmem_ld_wait();                                               // chunk c is in registers
+                    if (c + 1 < kNC) {
+                        tmem_ld32_issue(taddr + (c + 1) * 32, vn);               // chunk c+1 streams in behind the math
+                    } else {
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty_bar[acc]);                        // every TMEM read of this tile has completed:
+                    }                                                             // accumulator free for tile it+2
+                    bias_act32<ACT>(v, bias_t + c * 32);
+                    if (p.mul != nullptr && m_ok) {
+                        const float* mp = p.mul + static_cast<size_t>(m) * p.ld_mul + nc;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
+                    }
+                    if (m_ok) store_chunk<F16>(p, m, nc, st_fast && nc + 32 <= p.N, v);
+                }
+                if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
+            } else {
+                // ------------------------------------------------ LayerNorm epilogue: 8 warps, row slice in registers
+                constexpr int kCPT = Cfg::kCPT;
+                const int c_begin = half * kCPT;                                  // this thread's chunks [c_begin, c_end)
+                const int c_end = (c_begin + kCPT < kNC) ? c_begin + kCPT : kNC;
+                const int my_cols = (c_end - c_begin) * 32;
+                const bool has_res = p.res != nullptr && m_ok;
+                float x[kCPT][32];
+                float4 rcur[8];
+                if (has_res) res_load(p, m, n0 + c_begin * 32, true, rcur);       // in flight while the MMAs run
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+                if (stamp) stamps[4] = clock64();
+#pragma unroll
+                for (int i = 0; i < kCPT; ++i)
+                    if (c_begin + i < c_end) tmem_ld32_issue(taddr + (c_begin + i) * 32, x[i]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tmem_empty_bar[acc]);                                // TMEM read once; hand the accumulator back
+                float lsum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kCPT; ++i) {
+                    if (c_begin + i < c_end) {
+                        if (has_res) {
+                            res_add(x[i], rcur);
+                            // next chunk's residual reuses the same registers and flies behind this chunk's bias / GELU
+                            if (i + 1 < kCPT && c_begin + i + 1 < c_end) res_load(p, m, n0 + (c_begin + i + 1) * 32, true, rcur);
+                        }
+                        bias_act32<ACT>(x[i], s_bias + (c_begin + i) * 32);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) lsum += x[i][j];
+                    }
+                }
+                const float lmean = lsum / static_cast<float>(my_cols);
+                float m2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kCPT; ++i) {
+                    if (c_begin + i < c_end) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { const float d = x[i][j] - lmean; m2 = fmaf(d, d, m2); }
+                    }
+                }
+                if (stamp) stamps[5] = clock64();
+                // ---- ONE exchange of (mean_local, M2_local) per row, column half and CTA
+                float2* part = s_part + (it & 1u) * (2 * kBlockM);                // double-buffered across tiles
+                part[half * kBlockM + row] = make_float2(lmean, m2);
+                __syncwarp();
+                uint64_t* lb = &ln_bar[it & 1u];
+                if (lane == 0)
+                    for (uint32_t rk = 0; rk < cluster_size; ++rk) mbar_arrive_remote_release(mapa_u32(lb, rk));
+                mbar_wait_acquire_cluster(lb, (it >> 1) & 1u);                    // every CTA's partials for this tile are visible
+                constexpr float kColsH0 = static_cast<float>(kCPT * 32);          // columns of half 0
+                constexpr float kColsH1 = static_cast<float>(BLOCK_N - kCPT * 32);  // columns of half 1
+                float2 pr0[8], pr1[8];
+#pragma unroll
+                for (uint32_t rk = 0; rk < 8; ++rk) {
+                    if (rk < cluster_size) {
+                        pr0[rk] = dsmem_ld_f32x2(mapa_u32(&part[row], rk));
+                        pr1[rk] = dsmem_ld_f32x2(mapa_u32(&part[kBlockM + row], rk));
+                    }
+                }
+                float tot = 0.0f;
+#pragma unroll
+                for (uint32_t rk = 0; rk < 8; ++rk)
+                    if (rk < cluster_size) tot += pr0[rk].x * kColsH0 + pr1[rk].x * kColsH1;
+                const float mean = tot / static_cast<float>(p.N);
+                float M2 = 0.0f;
+#pragma unroll
+                for (uint32_t rk = 0; rk < 8; ++rk) {
+                    if (rk < cluster_size) {
+                        const float d0 = pr0[rk].x - mean, d1 = pr1[rk].x - mean;
+                        M2 += pr0[rk].y + kColsH0 * d0 * d0 + pr1[rk].y + kColsH1 * d1 * d1;
+                    }
+                }
+                const float rstd = 1.0f / sqrtf(M2 / static_cast<float>(p.N) + p.eps);
+                if (stamp) stamps[6] = clock64();
+#pragma unroll
+                for (int i = 0; i < kCPT; ++i) {
+                    if (c_begin + i < c_end) {
+                        const int cc = (c_begin + i) * 32;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 g = reinterpret_cast<const float4*>(s_gamma + cc)[j4];
+                            const float4 b = reinterpret_cast<const float4*>(s_beta + cc)[j4];
+                            x[i][4 * j4 + 0] = (x[i][4 * j4 + 0] - mean) * rstd * g.x + b.x;
+                            x[i][4 * j4 + 1] = (x[i][4 * j4 + 1] - mean) * rstd * g.y + b.y;
+                            x[i][4 * j4 + 2] = (x[i][4 * j4 + 2] - mean) * rstd * g.z + b.z;
+                            x[i][4 * j4 + 3] = (x[i][4 * j4 + 3] - mean) * rstd * g.w + b.w;
+                        }
+                        if (m_ok) store_chunk<F16>(p, m, n0 + cc, true, x[i]);         // LN output strides are validated on the host
+                    }
+                }
+                if (stamp) stamps[7] = clock64();
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- teardown
+    tc_fence_before();
+    if (LN) cluster_sync_all(); else __syncthreads();     // LN: nobody exits while a peer may still read its partials
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+
+// --------------------------------------------------------------------------------------------- host side (shared)
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N, bool LN>
+void fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, dim3 grid, int cluster, int pdl, cudaStream_t st) {
+    using Cfg = PCfg<BLOCK_N, LN>;
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    unsigned na = 0;
+    if (LN) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = cluster;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+}
+
+// resident: LN only -- how many clusters of this size can be co-resident (grid.y is capped to it)
+template <int BLOCK_N, bool LN, int ACT, bool F16>
+cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int resident, cudaStream_t st) {
+    using Cfg = PCfg<BLOCK_N, LN>;
+    auto kern = gemm_persistent_kernel<BLOCK_N, LN, ACT, F16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    const int n_tiles = (ep.N + BLOCK_N - 1) / BLOCK_N;
+    const int m_tiles = (ep.M + kBlockM - 1) / kBlockM;
+    dim3 grid;
+    int cluster = 1;
+    if (LN) {
+        cluster = n_tiles;
+        if (resident <= 0) return cudaErrorInvalidConfiguration;
+        grid = dim3(cluster, std::min(m_tiles, resident), 1);
+    } else {
+        grid = dim3(std::min(m_tiles * n_tiles, num_sms() * Cfg::kMinBlocks), 1, 1);
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+    fill_cfg<BLOCK_N, LN>(cfg, attrs, grid, cluster, ep.pdl, st);
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, m_tiles, n_tiles);
+}
+
+}  // namespace pgemm
+}  // namespace vb

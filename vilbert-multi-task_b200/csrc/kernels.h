@@ -37,6 +37,8 @@ int gemm_p_pick_block_n(int N, bool ln);
 int gemm_p_max_clusters(int block_n, int cluster);
 cudaError_t launch_gemm_persistent(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep,
                                    int block_n, bool ln, cudaStream_t st);
+cudaError_t launch_gemm_persistent_plain(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep,
+                                         int block_n, cudaStream_t st);
 
 // 16-bit activation buffers are typed __nv_bfloat16* throughout; `f16` says the bits are IEEE fp16 instead.
 // K4: softmax(Q K^T / sqrt(d) + mask) V per (sample, head); qkv row = [Q | K | V], each `hidden` wide.
