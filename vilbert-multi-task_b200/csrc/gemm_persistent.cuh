@@ -39,14 +39,19 @@ struct PCfg {
     static constexpr int kEpiThreads = 32 * kEpiWarps;
     static constexpr int kThreads = 64 + kEpiThreads;            // warp 0 TMA, warp 1 MMA (+TMEM alloc), then epilogue
     static constexpr int kMinBlocks = (LN || BLOCK_N >= 192) ? 1 : 2;
-    static constexpr int kFit = 200 * 1024 / kStageBytes;
+    // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
+    // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
+    //   plain: 32 rows x 20 words of packed 16-bit pairs;  LN: 32 rows x 33 fp32 (serves the fp32 and the 16-bit output)
+    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 32 * 20 * 4;
+    static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
+    static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
     static constexpr int kStages = kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit);
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     // LN: chunks per epilogue thread (two column halves per TMEM lane quarter)
     static constexpr int kCPT = (kNumChunks + 1) / 2;
     // ring | bias[2][BLOCK_N] gamma beta (4*BLOCK_N f32) | part[2 bufs][2 halves][128] float2 | barriers | tmem ptr
     static constexpr int kNumBars = 2 * kStages + 4 + 2;
-    static constexpr int kSmemAux = 4 * BLOCK_N * 4 + 4 * kBlockM * 8 + kNumBars * 8 + 16;
+    static constexpr int kSmemAux = 4 * BLOCK_N * 4 + 4 * kBlockM * 8 + kNumBars * 8 + 16 + kXposeBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux + 1024;
 };
 
@@ -177,6 +182,68 @@ __device__ __forceinline__ void res_add(float (&v)[32], const float4 (&r)[8]) {
     for (int j = 0; j < 8; ++j) { v[4 * j] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w; }
 }
 
+// ---- row-contiguous stores through a per-warp shared-memory transpose
+// 16-bit output of one 32-row x 32-column chunk held row-per-lane in v: pack, transpose, then every store instruction
+// writes 8 rows x 64 contiguous bytes (2 full sectors per row) instead of 32 rows x 16 bytes.
+template <bool F16>
+__device__ __forceinline__ void store16_coalesced(uint32_t* st, __nv_bfloat16* out, int ld, int m_warp, int M, int ncol,
+                                                  const float (&v)[32], int lane) {
+    constexpr int S = 20;                                  // words per staged row (16 used): 16-byte accesses stay conflict-free
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = F16 ? pack16x2_rt(v[8 * j + 0], v[8 * j + 1], 1) : pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = F16 ? pack16x2_rt(v[8 * j + 2], v[8 * j + 3], 1) : pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = F16 ? pack16x2_rt(v[8 * j + 4], v[8 * j + 5], 1) : pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = F16 ? pack16x2_rt(v[8 * j + 6], v[8 * j + 7], 1) : pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(st + lane * S + 4 * j) = u;
+    }
+    __syncwarp();
+    const int piece = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        const uint4 u = *reinterpret_cast<const uint4*>(st + r * S + 4 * piece);
+        if (m_warp + r < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(m_warp + r) * ld + ncol + piece * 8) = u;
+    }
+    __syncwarp();                                          // staging buffer is reused by the next chunk
+}
+// LayerNorm outputs (fp32 stream copy and 16-bit GEMM operand) of one chunk from an fp32 [32][33] transpose buffer.
+template <bool F16>
+__device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue& p, int m_warp, int ncol, const float (&v)[32],
+                                                   int lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
+    __syncwarp();
+    if (p.out_f32 != nullptr) {
+        const int c4 = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {                   // 4 rows x 128 contiguous bytes per instruction
+            const int r = it * 4 + (lane >> 3);
+            const float* s4 = st + r * 33 + c4 * 4;
+            if (m_warp + r < p.M)
+                *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m_warp + r) * p.ld_f32 + ncol + c4 * 4) =
+                    make_float4(s4[0], s4[1], s4[2], s4[3]);
+        }
+    }
+    if (p.out_bf16 != nullptr) {
+        const int piece = lane & 3;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {                   // 8 rows x 64 contiguous bytes per instruction
+            const int r = it * 8 + (lane >> 2);
+            const float* s8 = st + r * 33 + piece * 8;
+            uint4 u;
+            u.x = F16 ? pack16x2_rt(s8[0], s8[1], 1) : pack_bf16x2(s8[0], s8[1]);
+            u.y = F16 ? pack16x2_rt(s8[2], s8[3], 1) : pack_bf16x2(s8[2], s8[3]);
+            u.z = F16 ? pack16x2_rt(s8[4], s8[5], 1) : pack_bf16x2(s8[4], s8[5]);
+            u.w = F16 ? pack16x2_rt(s8[6], s8[7], 1) : pack_bf16x2(s8[6], s8[7]);
+            if (m_warp + r < p.M)
+                *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(m_warp + r) * p.ld_bf16 + ncol + piece * 8) = u;
+        }
+    }
+    __syncwarp();
+}
+
 template <int BLOCK_N, bool LN, int ACT, bool F16>
 __global__ void __launch_bounds__(PCfg<BLOCK_N, LN>::kThreads, PCfg<BLOCK_N, LN>::kMinBlocks)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -201,6 +268,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint64_t* ln_bar = tmem_empty_bar + 2;             // [2] cluster exchange, alternating per tile so that arrivals
                                                        //     for tile i+1 can never be counted into tile i's phase
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ln_bar + 2);
+    uint8_t* s_xpose = reinterpret_cast<uint8_t*>(tmem_ptr_smem + 4);               // [kEpiWarps][kXposeBytesPerWarp]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -312,6 +380,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;
         const bool st_fast = (p.out_bf16 == nullptr || (p.ld_bf16 & 7) == 0) && (p.out_f32 == nullptr || (p.ld_f32 & 3) == 0);
+        const bool coalesce16 = !LN && p.out_bf16 != nullptr && p.out_f32 == nullptr && p.mul == nullptr && (p.ld_bf16 & 7) == 0;
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -352,7 +421,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
                     }
-                    if (m_ok) store_chunk<F16>(p, m, nc, st_fast && nc + 32 <= p.N, v);
+                    if (coalesce16 && nc + 32 <= p.N)              // warp-uniform: the common 16-bit-only GEMM outputs
+                        store16_coalesced<F16>(reinterpret_cast<uint32_t*>(s_xpose + ew * Cfg::kXposeBytesPerWarp), p.out_bf16,
+                                               p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
+                    else if (m_ok) store_chunk<F16>(p, m, nc, st_fast && nc + 32 <= p.N, v);
                 }
                 if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
             } else {
@@ -444,7 +516,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             x[i][4 * j4 + 2] = (x[i][4 * j4 + 2] - mean) * rstd * g.z + b.z;
                             x[i][4 * j4 + 3] = (x[i][4 * j4 + 3] - mean) * rstd * g.w + b.w;
                         }
-                        if (m_ok) store_chunk<F16>(p, m, n0 + cc, true, x[i]);         // LN output strides are validated on the host
+                        store_ln_coalesced<F16>(reinterpret_cast<float*>(s_xpose + ew * Cfg::kXposeBytesPerWarp), p, m0 + q * 32,
+                                                n0 + cc, x[i], lane);                  // output strides are validated on the host
                     }
                 }
                 if (stamp) stamps[7] = clock64();
