@@ -6,7 +6,7 @@ echo "ops exit $?" >> gpurun_out/status.txt
 timeout 600 python scripts/kernel_bench.py --stamps > gpurun_out/kernel_bench.log 2>&1
 echo "kb exit $?" >> gpurun_out/status.txt
 timeout 600 python scripts/kernel_bench.py --variant 1 > gpurun_out/kernel_bench_v1.log 2>&1
-timeout 600 python scripts/kernel_bench.py --batch 512 --reps 20 > gpurun_out/kernel_bench_b512.log 2>&1
+timeout 600 python scripts/kernel_bench.py --batch 512 --reps 100 > gpurun_out/kernel_bench_b512.log 2>&1
 timeout 1500 python -m pytest tests/test_gpu_model.py -m gpu -q --timeout=900 -p no:cacheprovider > gpurun_out/pytest_model.log 2>&1
 echo "model exit $?" >> gpurun_out/status.txt
 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1

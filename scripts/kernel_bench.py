@@ -19,10 +19,32 @@ def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def time_graph(run, reps, n_in_graph=20):
+    """True GPU time per launch: the launches are captured once into a CUDA graph and replayed, so neither Python, ctypes,
+    cuTensorMapEncode nor cudaFuncSetAttribute sit between kernels (an eager loop of ~7 us kernels is host-bound)."""
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n_in_graph):
+            run(i)
+    g.replay()
+    torch.cuda.synchronize()
+    n = max(1, reps // n_in_graph)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (n * n_in_graph)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
-    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--act", default="fp16")
     ap.add_argument("--sets", type=int, default=4, help="operand sets cycled through per kernel")
@@ -34,7 +56,7 @@ def main():
     Mt, Mv = B * T, B * V
     act = torch.float16 if a.act == "fp16" else torch.bfloat16
     f16 = 1 if a.act == "fp16" else 0
-    st = torch.cuda.current_stream().cuda_stream
+    cur = lambda: torch.cuda.current_stream().cuda_stream      # the capture stream while a graph is being recorded
     g = torch.Generator(device="cuda").manual_seed(0)
     # name, M, N, K, act, residual+LN, block_n
     gemms = [
@@ -66,18 +88,9 @@ def main():
         def run(i):
             x, w, b, r, ga, be, yb, yf, ldf = sets[i % a.sets]
             rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
-                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, None, C.c_void_p(st))
+                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, None, C.c_void_p(cur()))
             L.check(rc, None)
-        for i in range(5):
-            run(i)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(a.reps):
-            run(i)
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / a.reps
+        us = time_graph(run, a.reps)
         fl = 2.0 * M * N * K
         res.append(dict(kernel=name, M=M, N=N, K=K, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
         print(json.dumps(res[-1]), flush=True)
@@ -85,7 +98,7 @@ def main():
             tb = torch.zeros(16 * 4096, dtype=torch.int64, device="cuda")
             x, w, b, r, ga, be, yb, yf, ldf = sets[0]
             rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
-                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, 0, ptr(tb), C.c_void_p(st))
+                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, 0, ptr(tb), C.c_void_p(cur()))
             L.check(rc, None)
             torch.cuda.synchronize()
             t = tb.view(-1, 16).cpu()
@@ -106,17 +119,8 @@ def main():
         ctx = torch.empty(B * Lq, H, dtype=act, device="cuda")
 
         def run(i):
-            L.check(lib.vb200_self_attention(ptr(qkv), 3 * H, H, ptr(mask), ptr(ctx), H, B, Lq, heads, d, f16, C.c_void_p(st)), None)
-        for i in range(5):
-            run(i)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(a.reps):
-            run(i)
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / a.reps
+            L.check(lib.vb200_self_attention(ptr(qkv), 3 * H, H, ptr(mask), ptr(ctx), H, B, Lq, heads, d, f16, C.c_void_p(cur())), None)
+        us = time_graph(run, a.reps)
         print(json.dumps(dict(kernel=name, us=round(us, 2))), flush=True)
     if not a.only or "co_attn" in a.only:
         H = 1024
@@ -127,17 +131,8 @@ def main():
 
         def run(i):
             L.check(lib.vb200_co_attention(ptr(qi), 3 * H, ptr(qt), 3 * H, H, ptr(mi), ptr(mt), ptr(ct), H, ptr(ci), H,
-                                           B, T, V, 8, 128, f16, C.c_void_p(st)), None)
-        for i in range(5):
-            run(i)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(a.reps):
-            run(i)
-        e1.record()
-        torch.cuda.synchronize()
-        print(json.dumps(dict(kernel="co_attn", us=round(e0.elapsed_time(e1) * 1e3 / a.reps, 2))), flush=True)
+                                           B, T, V, 8, 128, f16, C.c_void_p(cur())), None)
+        print(json.dumps(dict(kernel="co_attn", us=round(time_graph(run, a.reps), 2))), flush=True)
 
 
 if __name__ == "__main__":

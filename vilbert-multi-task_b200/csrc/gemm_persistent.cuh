@@ -298,7 +298,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
             mbar_init(&tmem_empty_bar[a], kEpiThreads);
-            mbar_init(&ln_bar[a], LN ? cluster_size * Cfg::kEpiWarps : 1u);   // one arrival per epilogue warp in the cluster
+            mbar_init(&ln_bar[a], LN ? cluster_size : 1u);                   // one arrival per CTA of the cluster
         }
         mbar_fence_init();
     } else if (warp == 1) {
@@ -473,10 +473,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 // ---- ONE exchange of (mean_local, M2_local) per row, column half and CTA
                 float2* part = s_part + (it & 1u) * (2 * kBlockM);                // double-buffered across tiles
                 part[half * kBlockM + row] = make_float2(lmean, m2);
-                __syncwarp();
+                epi_bar_sync<kEpiThreads>();                                     // this CTA's partials are all written
                 uint64_t* lb = &ln_bar[it & 1u];
-                if (lane == 0)
-                    for (uint32_t rk = 0; rk < cluster_size; ++rk) mbar_arrive_remote_release(mapa_u32(lb, rk));
+                // one release-arrive per (CTA, peer), issued by cluster_size lanes in parallel (serialising 8 remote arrives
+                // per warp in one lane cost ~6 k cycles); bar.sync ordered the other threads' writes before it
+                if (ew == 0 && lane < static_cast<int>(cluster_size)) mbar_arrive_remote_release(mapa_u32(lb, lane));
                 mbar_wait_acquire_cluster(lb, (it >> 1) & 1u);                    // every CTA's partials for this tile are visible
                 constexpr float kColsH0 = static_cast<float>(kCPT * 32);          // columns of half 0
                 constexpr float kColsH1 = static_cast<float>(BLOCK_N - kCPT * 32);  // columns of half 1
