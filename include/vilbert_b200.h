@@ -113,6 +113,10 @@ typedef struct {
                                       needs matching A/B formats).  default on: IEEE fp16 (11-bit significand; activations
                                       are LayerNorm-bounded, converts saturate); -1: bf16.  Accumulation, residual stream,
                                       LayerNorm, softmax and logits are fp32 either way. */
+    int32_t fused_layernorm;       /* default off: LayerNorm(dense(x) + residual) runs as GEMM (fp32 out) + an L2-resident row
+                                      kernel; 1: cluster-LayerNorm GEMM epilogue (N tiles of a row-panel form a thread-block
+                                      cluster and exchange (mean, M2) through distributed shared memory).  Both are
+                                      parity-tested; the split form measured faster on B200 at every batch tried. */
 } vb200_options;
 
 int vb200_abi_version(void);
@@ -149,6 +153,10 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
                  void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
                  int32_t block_n, int32_t use_pdl, int32_t act_fp16, int32_t variant, long long* timing, void* cuda_stream);
 /* ctx = softmax(Q K^T / sqrt(d) + mask) V, qkv rows = [Q | K | V] (bf16), mask_add fp32 [B, L]. */
+/* out = LayerNorm(y + residual) * gamma + beta over rows of N (N % 128 == 0, N <= 2048); fp32 and/or 16-bit outputs. */
+int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
+                    float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
+                    int32_t act_fp16, void* cuda_stream);
 int vb200_self_attention(const void* qkv_bf16, int64_t ld_qkv, int32_t hidden, const float* mask_add, void* ctx_bf16,
                          int64_t ld_ctx, int32_t B, int32_t L, int32_t heads, int32_t head_dim, int32_t act_fp16,
                          void* cuda_stream);

@@ -107,7 +107,11 @@ def main():
             names = ["entry", "setup", "first_kblock", "mma_issued", "acc_ready", "epi_pass1", "ln_exchange", "epi_done",
                      "c0_ld", "c0_res", "c0_math", "c0_store", "c1_ld", "c1_res", "c1_math", "c1_store"]
             print("   stamps (SM cycles since CTA entry, median over %d CTAs): " % len(t) +
-                  ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names) if (t[:, i] != 0).any()), flush=True)
+                  ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names[:8]) if (t[:, i] != 0).any()), flush=True)
+            g0, g1 = t[:, 8].double(), t[:, 9].double()
+            print(f"   globaltimer: kernel span {(g1.max() - g0.min()) / 1e3:.2f} us, CTA start spread {(g0.max() - g0.min()) / 1e3:.2f} us, "
+                  f"CTA lifetime median {(g1 - g0).median() / 1e3:.2f} us max {(g1 - g0).max() / 1e3:.2f} us, "
+                  f"end spread {(g1.max() - g1.min()) / 1e3:.2f} us", flush=True)
 
     attn = [("self_attn_text", 12, 64, T), ("self_attn_img", 8, 128, V)]
     for name, heads, d, Lq in attn:

@@ -38,7 +38,7 @@ def test_ctypes_structs_match_header_layout():
     assert C.sizeof(L.Tensor) == 8 + 4 + 4 + 16 + 8
     assert C.sizeof(L.Inputs) == 16 + 8 * 8
     assert C.sizeof(L.Outputs) == 12 * 8
-    assert C.sizeof(L.Options) == 24
+    assert C.sizeof(L.Options) == 28
 
 
 def _create(cfg, sd, **opt):

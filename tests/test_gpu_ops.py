@@ -226,3 +226,28 @@ def test_co_attention(B, T, V, heads, d, act_dt, parity_log):
     e2 = (ctx_i.view(B, V, H).float() - ref_i).abs().max().item()
     parity_log(test="co_attention", B=B, T=T, V=V, err_text_ctx=e1, err_image_ctx=e2)
     assert e1 < 2e-2 and e2 < 2e-2
+
+
+@pytest.mark.parametrize("act_dt", ACT)
+@pytest.mark.parametrize("M,N,with_res", [(1984, 768, True), (2304, 1024, True), (64, 2048, False), (37, 128, True), (5, 256, False)])
+def test_layernorm_row_kernel(M, N, with_res, act_dt, parity_log):
+    """vb200_layernorm: LayerNorm(y + residual) with fp32 and 16-bit outputs (the un-fused LayerNorm path)."""
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    y = torch.randn(M, N, generator=g, device="cuda") * 3 + 0.5
+    res = torch.randn(M, N, generator=g, device="cuda") if with_res else None
+    gamma = 1.0 + 0.1 * torch.randn(N, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(N, generator=g, device="cuda")
+    of = torch.empty(M, N, device="cuda")
+    oh = torch.empty(M, N, dtype=act_dt, device="cuda")
+    rc = lib.vb200_layernorm(_ptr(y), N, _ptr(res), N if with_res else 0, _ptr(gamma), _ptr(beta), 1e-12, _ptr(of), N, _ptr(oh), N,
+                             M, N, 1 if act_dt == torch.float16 else 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(rc, None)
+    torch.cuda.synchronize()
+    x = (y + res if with_res else y).double()
+    u = x.mean(-1, keepdim=True)
+    ref = ((x - u) / torch.sqrt((x - u).pow(2).mean(-1, keepdim=True) + 1e-12) * gamma.double() + beta.double()).float()
+    err = (of - ref).abs().max().item()
+    parity_log(test="layernorm_row", M=M, N=N, max_abs_err=err)
+    assert err < 1e-5
+    assert (oh.float() - ref).abs().max().item() < 5e-2

@@ -51,12 +51,13 @@ class Outputs(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_labels", C.c_int32), ("use_cuda_graph", C.c_int32),
-                ("use_pdl", C.c_int32), ("strict", C.c_int32), ("act_fp16", C.c_int32)]
+                ("use_pdl", C.c_int32), ("strict", C.c_int32), ("act_fp16", C.c_int32),
+                ("fused_layernorm", C.c_int32)]
 
 
 # every symbol include/vilbert_b200.h declares (tests/test_cabi.py checks the list against the header)
 EXPORTS = ["vb200_abi_version", "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_forward",
-           "vb200_forward_host", "vb200_plan_info", "vb200_model_dim", "vb200_linear",
+           "vb200_forward_host", "vb200_plan_info", "vb200_model_dim", "vb200_linear", "vb200_layernorm",
            "vb200_self_attention", "vb200_co_attention"]
 
 _lib = None
@@ -91,6 +92,7 @@ def load():
     lib.vb200_model_dim.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     lib.vb200_linear.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, f32, i32, vp, i64, vp, i64,
                                  i64, i64, i64, i32, i32, i32, i32, vp, vp]
+    lib.vb200_layernorm.argtypes = [vp, i64, vp, i64, vp, vp, f32, vp, i64, vp, i64, i64, i64, i32, vp]
     lib.vb200_self_attention.argtypes = [vp, i64, i32, vp, vp, i64, i32, i32, i32, i32, i32, vp]
     lib.vb200_co_attention.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     for name in EXPORTS:

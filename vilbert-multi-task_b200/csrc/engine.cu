@@ -295,7 +295,7 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
 
 // ------------------------------------------------------------------------------------------ launch list
 struct Op {
-    enum Kind { GEMM, SELF_ATTN, CO_ATTN, ROWDOT } kind;
+    enum Kind { GEMM, SELF_ATTN, CO_ATTN, ROWDOT, LAYERNORM } kind;
     int stream = 0;                // 0 main, 1 side (image branch) inside the captured graph
     // GEMM
     CUtensorMap ta, tb;
@@ -308,6 +308,11 @@ struct Op {
     const float *mask_a = nullptr, *mask_b = nullptr;
     bf16 *ctx_a = nullptr, *ctx_b = nullptr;
     int ld_ctx_a = 0, ld_ctx_b = 0, B = 0, La = 0, Lb = 0, heads = 0, head_dim = 0;
+    // layernorm (un-fused): out = LN(ln_y + ln_res)
+    const float *ln_y = nullptr, *ln_res = nullptr, *ln_g = nullptr, *ln_b = nullptr;
+    float* ln_out_f = nullptr;
+    bf16* ln_out_h = nullptr;
+    int ln_ld = 0, ln_M = 0, ln_N = 0;
     // rowdot
     const float *x = nullptr, *W = nullptr, *bias = nullptr, *add = nullptr;
     float* out = nullptr;
@@ -328,6 +333,7 @@ struct Plan {
     float *mask_t = nullptr, *mask_v = nullptr;
     float* t_f32[2]; bf16* t_b16[2];
     float* v_f32[2]; bf16* v_b16[2];
+    float* y_scratch[2] = {nullptr, nullptr};   // per-stream fp32 GEMM output feeding the un-fused LayerNorm kernel
     int t_cur = 0, v_cur = 0;
     std::vector<Op> ops;
     OutBuf outs[12];
@@ -354,6 +360,7 @@ struct vb200_engine {
     int num_labels = 0, gqa_labels = 0;
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
+    bool fused_ln = false;     // VB200_FUSED_LN=1: cluster-LayerNorm GEMM epilogue instead of GEMM(fp32) + row LayerNorm kernel
     Arena weights;
     std::string last_error;
     // embeddings
@@ -602,26 +609,48 @@ struct vb200_engine {
     }
 
     // ---------------------------------------------------------------- plan construction
-    Op gemm_op(Plan& pl, const bf16* A, int64_t a_rows, int64_t lda, const LinearW& W, int act, const float* res, int ld_res,
-               const LNW* ln, bf16* out_b, int ld_b, float* out_f, int ld_f, const float* mul = nullptr, int ld_mul = 0, int stream = 0) {
+    // One nn.Linear (+ activation, + residual LayerNorm) -> one or two launch-list entries on `stream`.
+    //   fused_ln:  a single cluster-LayerNorm GEMM (epilogue normalises across the N tiles of a cluster)
+    //   default :  GEMM (+bias, +activation) writing fp32 to the stream's scratch, then the row LayerNorm kernel
+    //              (adds the residual) -- measured faster at every batch size tried (profiles/).
+    void add_linear(Plan& pl, const bf16* A, int64_t a_rows, int64_t lda, const LinearW& W, int act, const float* res, int ld_res,
+                    const LNW* ln, bf16* out_b, int ld_b, float* out_f, int ld_f, int stream = 0, Op::Sync sync = Op::NONE,
+                    const float* mul = nullptr, int ld_mul = 0) {
+        const bool split_ln = ln != nullptr && !fused_ln;
         Op op{};
         op.kind = Op::GEMM;
         op.stream = stream;
-        op.ln = ln != nullptr;
+        op.sync = sync;
+        op.ln = ln != nullptr && !split_ln;
         op.block_n = gemm_v1 ? vb::gemm_pick_block_n(W.N, op.ln) : vb::gemm_p_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
         op.ta = make_tmap(A, a_rows, W.ldw, lda, 128, opt.act_fp16 != 0);
         op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.block_n, opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
-        e.bias = W.bias; e.res = res; e.ld_res = ld_res; e.mul = mul; e.ld_mul = ld_mul;
-        e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr; e.eps = cfg.ln_eps;
-        e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f; e.act = act; e.pdl = opt.use_pdl;
+        e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = opt.use_pdl;
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
+        if (split_ln) {
+            float* y = pl.y_scratch[stream];
+            e.out_f32 = y; e.ld_f32 = W.N;
+        } else {
+            e.res = res; e.ld_res = ld_res;
+            e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr;
+            e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f;
+        }
         op.flops = 2.0 * a_rows * W.N * W.K;
         pl.flops += op.flops;
-        (void)pl;
-        return op;
+        pl.ops.push_back(op);
+        if (split_ln) {
+            Op l{};
+            l.kind = Op::LAYERNORM;
+            l.stream = stream;
+            l.ln_y = pl.y_scratch[stream]; l.ln_res = res; l.ld_x = ld_res;
+            l.ln_g = ln->g; l.ln_b = ln->b; l.ln_out_f = out_f; l.ln_out_h = out_b; l.ln_ld = W.N;
+            l.ld_out = out_f ? ld_f : 0; l.ld_a = out_b ? ld_b : 0;
+            l.ln_M = static_cast<int>(a_rows); l.ln_N = W.N;
+            pl.ops.push_back(l);
+        }
     }
     Op rowdot_op(const float* x, int ld_x, const RowW& w, const float* add, float* out, int ld_out, int M) {
         Op op{};
@@ -660,6 +689,11 @@ struct vb200_engine {
             pl.v_f32[i] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv);
             pl.v_b16[i] = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * Hv);
         }
+        if (!fused_ln) {
+            const size_t n0 = std::max({static_cast<size_t>(Mt) * H, static_cast<size_t>(Mv) * Hv, static_cast<size_t>(B) * 2 * Hb});
+            pl.y_scratch[0] = pl.mem.alloc_n<float>(n0);
+            pl.y_scratch[1] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv);
+        }
         const int qt = 3 * std::max(H, Hb), qv = 3 * std::max(Hv, Hb);
         bf16* qkv_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * qt);
         bf16* qkv_v = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * qv);
@@ -670,25 +704,24 @@ struct vb200_engine {
         auto& ops = pl.ops;
 
         // ---- image embedding: LayerNorm(feat.W_img^T + loc.W_loc^T + b) as ONE GEMM over K = v_feat + 64
-        ops.push_back(gemm_op(pl, pl.img_a, Mv, pl.kp, img_emb, vb::kActNone, nullptr, 0, &vemb_ln, pl.v_b16[0], Hv, pl.v_f32[0], Hv));
-        ops.back().stream = 1;   // overlaps the text layers that precede the first co-attention
+        add_linear(pl, pl.img_a, Mv, pl.kp, img_emb, vb::kActNone, nullptr, 0, &vemb_ln, pl.v_b16[0], Hv, pl.v_f32[0], Hv,
+                   1);           // side stream: overlaps the text layers that precede the first co-attention
         int tc = 0, vc = 0;
 
         auto single_layer = [&](const LayerW& L, int M, int hid, int inter, int heads, float** f32, bf16** b16, int& cur,
                                 bf16* qkv, bf16* ctx, bf16* inter_buf, const float* mask, int seq, int stream) {
-            const size_t first = ops.size();
-            ops.push_back(gemm_op(pl, b16[cur], M, hid, L.qkv, vb::kActNone, nullptr, 0, nullptr, qkv, 3 * hid, nullptr, 0));
+            add_linear(pl, b16[cur], M, hid, L.qkv, vb::kActNone, nullptr, 0, nullptr, qkv, 3 * hid, nullptr, 0, stream);
             Op a{};
             a.kind = Op::SELF_ATTN;
+            a.stream = stream;
             a.qkv_a = qkv; a.ld_a = 3 * hid; a.hidden = hid; a.mask_a = mask; a.ctx_a = ctx; a.ld_ctx_a = hid;
             a.B = B; a.La = seq; a.heads = heads; a.head_dim = hid / heads;
             a.flops = 4.0 * B * heads * seq * seq * (hid / heads);
             pl.flops += a.flops;
             ops.push_back(a);
-            ops.push_back(gemm_op(pl, ctx, M, hid, L.attn_out, vb::kActNone, f32[cur], hid, &L.ln1, b16[1 - cur], hid, f32[1 - cur], hid));
-            ops.push_back(gemm_op(pl, b16[1 - cur], M, hid, L.inter, vb::kActGelu, nullptr, 0, nullptr, inter_buf, inter, nullptr, 0));
-            ops.push_back(gemm_op(pl, inter_buf, M, inter, L.out, vb::kActNone, f32[1 - cur], hid, &L.ln2, b16[cur], hid, f32[cur], hid));
-            for (size_t i = first; i < ops.size(); ++i) ops[i].stream = stream;
+            add_linear(pl, ctx, M, hid, L.attn_out, vb::kActNone, f32[cur], hid, &L.ln1, b16[1 - cur], hid, f32[1 - cur], hid, stream);
+            add_linear(pl, b16[1 - cur], M, hid, L.inter, vb::kActGelu, nullptr, 0, nullptr, inter_buf, inter, nullptr, 0, stream);
+            add_linear(pl, inter_buf, M, inter, L.out, vb::kActNone, f32[1 - cur], hid, &L.ln2, b16[cur], hid, f32[cur], hid, stream);
         };
 
         for (const std::string& step : schedule) {
@@ -699,10 +732,8 @@ struct vb200_engine {
                 single_layer(v_layers[idx], Mv, Hv, c.v_inter, c.v_heads, pl.v_f32, pl.v_b16, vc, qkv_v, ctx_v, inter_v, pl.mask_v, V, 1);
             } else {
                 const ConnW& W = c_layers[idx];
-                Op q1 = gemm_op(pl, pl.v_b16[vc], Mv, Hv, W.qkv_img, vb::kActNone, nullptr, 0, nullptr, qkv_v, 3 * Hb, nullptr, 0);
-                q1.stream = 1;
-                ops.push_back(q1);
-                ops.push_back(gemm_op(pl, pl.t_b16[tc], Mt, H, W.qkv_txt, vb::kActNone, nullptr, 0, nullptr, qkv_t, 3 * Hb, nullptr, 0));
+                add_linear(pl, pl.v_b16[vc], Mv, Hv, W.qkv_img, vb::kActNone, nullptr, 0, nullptr, qkv_v, 3 * Hb, nullptr, 0, 1);
+                add_linear(pl, pl.t_b16[tc], Mt, H, W.qkv_txt, vb::kActNone, nullptr, 0, nullptr, qkv_t, 3 * Hb, nullptr, 0, 0);
                 Op a{};
                 a.kind = Op::CO_ATTN;
                 a.sync = Op::JOIN;              // needs both projections
@@ -712,20 +743,14 @@ struct vb200_engine {
                 a.flops = 8.0 * B * c.bi_heads * T * V * (Hb / c.bi_heads);
                 pl.flops += a.flops;
                 ops.push_back(a);
-                // image branch (side stream)
-                Op d1 = gemm_op(pl, ctx_v, Mv, Hb, W.dense1, vb::kActNone, pl.v_f32[vc], Hv, &W.ln1, pl.v_b16[1 - vc], Hv, pl.v_f32[1 - vc], Hv);
-                d1.stream = 1; d1.sync = Op::FORK;
-                ops.push_back(d1);
-                Op vi = gemm_op(pl, pl.v_b16[1 - vc], Mv, Hv, W.v_inter, vb::kActGelu, nullptr, 0, nullptr, inter_v, c.v_inter, nullptr, 0);
-                vi.stream = 1;
-                ops.push_back(vi);
-                Op vo = gemm_op(pl, inter_v, Mv, c.v_inter, W.v_out, vb::kActNone, pl.v_f32[1 - vc], Hv, &W.v_ln, pl.v_b16[vc], Hv, pl.v_f32[vc], Hv);
-                vo.stream = 1;
-                ops.push_back(vo);
+                // image branch (side stream; forks from the co-attention)
+                add_linear(pl, ctx_v, Mv, Hb, W.dense1, vb::kActNone, pl.v_f32[vc], Hv, &W.ln1, pl.v_b16[1 - vc], Hv, pl.v_f32[1 - vc], Hv, 1, Op::FORK);
+                add_linear(pl, pl.v_b16[1 - vc], Mv, Hv, W.v_inter, vb::kActGelu, nullptr, 0, nullptr, inter_v, c.v_inter, nullptr, 0, 1);
+                add_linear(pl, inter_v, Mv, c.v_inter, W.v_out, vb::kActNone, pl.v_f32[1 - vc], Hv, &W.v_ln, pl.v_b16[vc], Hv, pl.v_f32[vc], Hv, 1);
                 // text branch (main stream)
-                ops.push_back(gemm_op(pl, ctx_t, Mt, Hb, W.dense2, vb::kActNone, pl.t_f32[tc], H, &W.ln2, pl.t_b16[1 - tc], H, pl.t_f32[1 - tc], H));
-                ops.push_back(gemm_op(pl, pl.t_b16[1 - tc], Mt, H, W.t_inter, vb::kActGelu, nullptr, 0, nullptr, inter_t, c.inter, nullptr, 0));
-                ops.push_back(gemm_op(pl, inter_t, Mt, c.inter, W.t_out, vb::kActNone, pl.t_f32[1 - tc], H, &W.t_ln, pl.t_b16[tc], H, pl.t_f32[tc], H));
+                add_linear(pl, ctx_t, Mt, Hb, W.dense2, vb::kActNone, pl.t_f32[tc], H, &W.ln2, pl.t_b16[1 - tc], H, pl.t_f32[1 - tc], H, 0);
+                add_linear(pl, pl.t_b16[1 - tc], Mt, H, W.t_inter, vb::kActGelu, nullptr, 0, nullptr, inter_t, c.inter, nullptr, 0, 0);
+                add_linear(pl, inter_t, Mt, c.inter, W.t_out, vb::kActNone, pl.t_f32[1 - tc], H, &W.t_ln, pl.t_b16[tc], H, pl.t_f32[tc], H, 0);
             }
         }
         pl.t_cur = tc; pl.v_cur = vc;
@@ -735,19 +760,17 @@ struct vb200_engine {
         float* pooled = pl.mem.alloc_n<float>(static_cast<size_t>(B) * Hb);
         bf16* pooled_b = pl.mem.alloc_n<bf16>(static_cast<size_t>(B) * Hb);
         {
-            Op p1 = gemm_op(pl, pl.t_b16[tc], B, static_cast<int64_t>(T) * H, t_pool, vb::kActRelu, nullptr, 0, nullptr, nullptr, 0, pooled_t, Hb);
-            p1.sync = Op::JOIN;
-            ops.push_back(p1);
-            ops.push_back(gemm_op(pl, pl.v_b16[vc], B, static_cast<int64_t>(V) * Hv, v_pool, vb::kActRelu, nullptr, 0, nullptr, pooled_b, Hb, pooled, Hb, pooled_t, Hb));
+            add_linear(pl, pl.t_b16[tc], B, static_cast<int64_t>(T) * H, t_pool, vb::kActRelu, nullptr, 0, nullptr, nullptr, 0, pooled_t, Hb, 0, Op::JOIN);
+            add_linear(pl, pl.v_b16[vc], B, static_cast<int64_t>(V) * Hv, v_pool, vb::kActRelu, nullptr, 0, nullptr, pooled_b, Hb, pooled, Hb, 0, Op::NONE, pooled_t, Hb);
         }
         pl.outs[11] = OutBuf{pooled, B, Hb, Hb};
         pl.outs[9] = OutBuf{pl.t_f32[tc], Mt, H, H};
         pl.outs[10] = OutBuf{pl.v_f32[vc], Mv, Hv, Hv};
         auto cls_head = [&](const ClsW& w, int n_out, int slot) {
             bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(B) * 2 * Hb);
-            ops.push_back(gemm_op(pl, pooled_b, B, Hb, w.fc0, vb::kActGelu, nullptr, 0, &w.ln, hid, 2 * Hb, nullptr, 0));
+            add_linear(pl, pooled_b, B, Hb, w.fc0, vb::kActGelu, nullptr, 0, &w.ln, hid, 2 * Hb, nullptr, 0);
             pl.outs[slot] = make_out(pl, B, n_out);
-            ops.push_back(gemm_op(pl, hid, B, 2 * Hb, w.fc3, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[slot].p, pl.outs[slot].ld));
+            add_linear(pl, hid, B, 2 * Hb, w.fc3, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[slot].p, pl.outs[slot].ld);
         };
         if (select & VB200_OUT_VIL_PREDICTION) cls_head(vqa, num_labels, 0);
         if (select & VB200_OUT_VIL_PREDICTION_GQA) cls_head(gqa, gqa_labels, 1);
@@ -759,7 +782,7 @@ struct vb200_engine {
             if (B % 2 == 0) {
                 // pooled.view(-1, 2*bi_hidden): adjacent samples form one NLVR2 pair (worker.py:266-276)
                 float* hid_f = pl.mem.alloc_n<float>(static_cast<size_t>(B / 2) * 2 * Hb);
-                ops.push_back(gemm_op(pl, pooled_b, B / 2, 2 * Hb, binary.fc0, vb::kActGelu, nullptr, 0, &binary.ln, nullptr, 0, hid_f, 2 * Hb));
+                add_linear(pl, pooled_b, B / 2, 2 * Hb, binary.fc0, vb::kActGelu, nullptr, 0, &binary.ln, nullptr, 0, hid_f, 2 * Hb);
                 pl.outs[3] = make_out(pl, B / 2, 2);
                 ops.push_back(rowdot_op(hid_f, 2 * Hb, binary.fc3_row, nullptr, pl.outs[3].p, pl.outs[3].ld, B / 2));
             } else {
@@ -774,9 +797,9 @@ struct vb200_engine {
         }
         if (select & VB200_OUT_VISION_PREDICTION) {
             bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * Hv);
-            ops.push_back(gemm_op(pl, pl.v_b16[vc], Mv, Hv, img_transform, vb::kActGelu, nullptr, 0, &img_ln, hid, Hv, nullptr, 0));
+            add_linear(pl, pl.v_b16[vc], Mv, Hv, img_transform, vb::kActGelu, nullptr, 0, &img_ln, hid, Hv, nullptr, 0);
             pl.outs[5] = make_out(pl, Mv, c.v_target);
-            ops.push_back(gemm_op(pl, hid, Mv, Hv, img_decoder, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[5].p, pl.outs[5].ld));
+            add_linear(pl, hid, Mv, Hv, img_decoder, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[5].p, pl.outs[5].ld);
         }
         if (select & VB200_OUT_VISION_LOGIT) {
             pl.outs[6] = make_out(pl, Mv, 1);
@@ -784,9 +807,9 @@ struct vb200_engine {
         }
         if (select & VB200_OUT_LINGUISIC_PREDICTION) {
             bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * H);
-            ops.push_back(gemm_op(pl, pl.t_b16[tc], Mt, H, lm_transform, vb::kActGelu, nullptr, 0, &lm_ln, hid, H, nullptr, 0));
+            add_linear(pl, pl.t_b16[tc], Mt, H, lm_transform, vb::kActGelu, nullptr, 0, &lm_ln, hid, H, nullptr, 0);
             pl.outs[7] = make_out(pl, Mt, c.vocab);
-            ops.push_back(gemm_op(pl, hid, Mt, H, lm_decoder, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[7].p, pl.outs[7].ld));
+            add_linear(pl, hid, Mt, H, lm_decoder, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[7].p, pl.outs[7].ld);
         }
         if (select & VB200_OUT_LINGUISIC_LOGIT) {
             pl.outs[8] = make_out(pl, Mt, 1);
@@ -825,6 +848,10 @@ struct vb200_engine {
                 CUDA_CHECK(vb::launch_co_attention(op.qkv_a, op.ld_a, op.qkv_b, op.ld_b, op.hidden, op.mask_a, op.mask_b, op.ctx_a,
                                                    op.ld_ctx_a, op.ctx_b, op.ld_ctx_b, op.B, op.La, op.Lb, op.heads, op.head_dim,
                                                    opt.use_pdl, opt.act_fp16, st));
+                break;
+            case Op::LAYERNORM:
+                CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
+                                                  op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, opt.use_pdl, st));
                 break;
             case Op::ROWDOT:
                 CUDA_CHECK(vb::launch_rowdot(op.x, op.ld_x, op.W, op.bias, op.add, op.out, op.ld_out, op.M, op.K, op.n_out, opt.use_pdl, st));
@@ -961,6 +988,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         o.strict = o.strict >= 0 ? 1 : 0;
         o.use_pdl = o.use_pdl > 0 ? 1 : 0;
         o.act_fp16 = o.act_fp16 >= 0 ? 1 : 0;
+        o.fused_layernorm = o.fused_layernorm > 0 ? 1 : 0;
         Config c = parse_config(config_json);
         {   // audit the state_dict (names, shapes, dtypes, strictness) before touching any device
             vb200_engine audit;
@@ -972,6 +1000,8 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->cfg = c;
         eng->opt = o;
         if (const char* v = getenv("VB200_GEMM")) eng->gemm_v1 = (strcmp(v, "v1") == 0);
+        eng->fused_ln = o.fused_layernorm != 0;
+        if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
@@ -1091,6 +1121,16 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
         e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16; e.timing = timing;
         if (variant == 1) CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
         else CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
+    });
+}
+
+int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
+                    float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
+                    int32_t act_fp16, void* cuda_stream) {
+    return op_guard([&] {
+        CUDA_CHECK(vb::launch_ln_residual(y, (int)ld_y, residual, (int)ld_res, gamma, beta, eps, out_f32, (int)ld_f32,
+                                          static_cast<bf16*>(out_16), (int)ld_16, (int)M, (int)N, act_fp16 ? 1 : 0, 0,
+                                          static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 

@@ -1,0 +1,83 @@
+// Residual-add + LayerNorm row kernel: x = y + res; out = (x - mean) / sqrt(var + eps) * gamma + beta, written as the
+// fp32 residual stream AND the 16-bit operand of the next GEMM.
+//
+// This is the un-fused alternative to the cluster-LayerNorm GEMM epilogue (gemm_persistent_ln.cu).  Measured on B200 at
+// the batch-64 shapes (profiles/): the fused epilogue needs a cluster-wide exchange plus ~2000 dependent instructions per
+// thread on 8 warps (~17 k cycles per 128x128 tile), while a plain tcgen05 GEMM that writes fp32 followed by this
+// L2-resident row kernel (one warp per row, 16-byte coalesced accesses, two-pass fp32 statistics in registers) is
+// faster end to end.  Replaces BertSelfOutput / BertOutput / BertBiOutput `LayerNorm(dense(x) + residual)` and the
+// LayerNorm inside SimpleClassifier ([UPSTREAM] vilbert/vilbert.py; anchor /root/reference/worker.py:286-289).
+#include "kernels.h"
+
+namespace vb {
+
+constexpr int kLnMaxVec = 16;   // N <= 2048: float4 per lane per 128 columns
+
+template <bool F16>
+__global__ void __launch_bounds__(256)
+ln_residual_kernel(const float* __restrict__ y, int ld_y, const float* __restrict__ res, int ld_res,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float* __restrict__ out_f32, int ld_f32, uint16_t* __restrict__ out16, int ld16, int M, int N, int pdl) {
+    if (pdl) { pdl_wait(); pdl_launch_dependents(); }
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int nvec = N >> 7;
+    const float4* yp = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * ld_y);
+    const float4* rp = res ? reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ld_res) : nullptr;
+    float4 x[kLnMaxVec];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+        if (k < nvec) {
+            float4 a = yp[lane + 32 * k];
+            if (rp) { const float4 r = rp[lane + 32 * k]; a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+            x[k] = a;
+            s += a.x + a.y + a.z + a.w;
+        }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(N);
+    float sq = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+        if (k < nvec) {
+            const float a = x[k].x - mean, b = x[k].y - mean, c = x[k].z - mean, d = x[k].w - mean;
+            sq += a * a + b * b + c * c + d * d;
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / static_cast<float>(N) + eps);
+    const float4* gp = reinterpret_cast<const float4*>(gamma);
+    const float4* bp = reinterpret_cast<const float4*>(beta);
+    float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * ld_f32) : nullptr;
+    uint2* oh = out16 ? reinterpret_cast<uint2*>(out16 + static_cast<size_t>(row) * ld16) : nullptr;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+        if (k < nvec) {
+            const float4 g = gp[lane + 32 * k], b = bp[lane + 32 * k];
+            float4 o;
+            o.x = (x[k].x - mean) * rstd * g.x + b.x;
+            o.y = (x[k].y - mean) * rstd * g.y + b.y;
+            o.z = (x[k].z - mean) * rstd * g.z + b.z;
+            o.w = (x[k].w - mean) * rstd * g.w + b.w;
+            if (of) of[lane + 32 * k] = o;
+            if (oh) oh[lane + 32 * k] = make_uint2(pack16x2<F16>(o.x, o.y), pack16x2<F16>(o.z, o.w));
+        }
+    }
+}
+
+cudaError_t launch_ln_residual(const float* y, int ld_y, const float* res, int ld_res, const float* gamma, const float* beta,
+                               float eps, float* out_f32, int ld_f32, __nv_bfloat16* out16, int ld16, int M, int N, int f16,
+                               int pdl, cudaStream_t st) {
+    if (N % 128 != 0 || N / 128 > kLnMaxVec || (ld_y & 3) || (res && (ld_res & 3)) || (out_f32 && (ld_f32 & 3)) ||
+        (out16 && (ld16 & 3)) || M < 1)
+        return cudaErrorInvalidValue;
+    const dim3 grid((M + 7) / 8), block(256);
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(out16);
+    if (f16)
+        return launch_ex(ln_residual_kernel<true>, grid, block, 0, pdl, st, y, ld_y, res, ld_res, gamma, beta, eps, out_f32,
+                         ld_f32, o16, ld16, M, N, pdl);
+    return launch_ex(ln_residual_kernel<false>, grid, block, 0, pdl, st, y, ld_y, res, ld_res, gamma, beta, eps, out_f32,
+                     ld_f32, o16, ld16, M, N, pdl);
+}
+
+}  // namespace vb

@@ -46,7 +46,8 @@ class VILBertForVLTasks(object):
     """Drop-in for ``vilbert.vilbert.VILBertForVLTasks`` on the inference path the worker uses."""
 
     def __init__(self, config: BertConfig, num_labels: int = 3129, state_dict=None, default_gpu: bool = True,
-                 use_cuda_graph: bool = True, use_pdl: bool = False, strict: bool = True, compute_dtype: str = "fp16"):
+                 use_cuda_graph: bool = True, use_pdl: bool = False, strict: bool = True, compute_dtype: str = "fp16",
+                 fused_layernorm: bool = False):
         self.config = config
         self.num_labels = num_labels
         self._sd = _normalise_state_dict(state_dict) if state_dict is not None else None
@@ -56,7 +57,8 @@ class VILBertForVLTasks(object):
             raise ValueError("compute_dtype must be 'fp16' or 'bf16'")
         # 16-bit format of the tensor-core operands (weights and activations); accumulation, residual stream,
         # LayerNorm, softmax and logits are fp32 in both modes
-        self._opts = dict(use_cuda_graph=use_cuda_graph, use_pdl=use_pdl, strict=strict, compute_dtype=compute_dtype)
+        self._opts = dict(use_cuda_graph=use_cuda_graph, use_pdl=use_pdl, strict=strict, compute_dtype=compute_dtype,
+                          fused_layernorm=fused_layernorm)
         self.training = False
         self._dims = {}
 
@@ -138,6 +140,7 @@ class VILBertForVLTasks(object):
         opt.use_pdl = 1 if self._opts["use_pdl"] else 0
         opt.strict = 1 if self._opts["strict"] else -1
         opt.act_fp16 = 1 if self._opts["compute_dtype"] == "fp16" else -1
+        opt.fused_layernorm = 1 if self._opts["fused_layernorm"] else 0
         h = C.c_void_p()
         with torch.cuda.device(device):
             rc = lib.vb200_create(self._config_json(), len(self._sd), arr, C.byref(opt), C.byref(h))
