@@ -42,6 +42,9 @@ def parse():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--pdl", action="store_true")
     p.add_argument("--all-heads", action="store_true", help="compute the seven task heads instead of VQA only")
+    p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
+                   help="16-bit format of the tensor-core operands (same tcgen05 rate; fp16 is the engine default, see DESIGN.md 2)")
+    p.add_argument("--fused-ln", action="store_true", help="cluster-LayerNorm GEMM epilogue instead of GEMM + row LayerNorm")
     return p.parse_args()
 
 
@@ -104,9 +107,12 @@ def oracle_model(sd, cfg_dict, num_labels):
     return m.eval()
 
 
+CPU_THREADS = min(16, os.cpu_count() or 1)   # measured on the 128-vCPU GPU box: 8 -> 56, 16 -> 78, 32 -> 44, 64 -> 23, 128 -> 0.2 pairs/s
+
+
 def time_oracle(model, req, steps, warmup):
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(CPU_THREADS)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -135,7 +141,7 @@ def run_reference(args):
     times = time_oracle(model, req, steps, max(1, min(args.warmup, 2)))
     total = sum(times)
     value = ref_batch * len(times) / total
-    cores = os.cpu_count() or 1
+    cores = CPU_THREADS
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -172,7 +178,8 @@ def run_b200(args):
     cfg = vb.BertConfig(task_specific_tokens=True, visualization=True)       # worker.py:509-522
     sd = S.synthetic_state_dict(cfg, seed=42)
     model = vb.VILBertForVLTasks.from_pretrained(sd, config=cfg, num_labels=3129, use_cuda_graph=not args.no_graph,
-                                                 use_pdl=args.pdl).eval().cuda(local_rank)
+                                                 use_pdl=args.pdl, compute_dtype=args.dtype,
+                                                 fused_layernorm=args.fused_ln).eval().cuda(local_rank)
     select = L.OUT_TASK_HEADS if args.all_heads else L.OUT_VIL_PREDICTION
     n_launch, flops = model.plan_info(B, Tin, V, select)
 
@@ -239,24 +246,48 @@ def run_b200(args):
 
     pk = peaks()
     tflops = flops * args.steps / (ms * 1e-3) / 1e12           # per GPU (ms is the max over ranks)
+    # ---- per-kernel times, live: every kernel of the step between two CUDA events on its launching stream (eager, one stream)
+    ops = model.profile_ops(B, Tin, V, select, iters=5)
+    fam = {}
+    for o in ops:
+        f = fam.setdefault(o["kind"], {"launches": 0, "ms": 0.0, "flops": 0.0})
+        f["launches"] += 1; f["ms"] += o["ms"]; f["flops"] += o["flops"]
+    g = fam["gemm"]
+    gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12
+    serial_ms = sum(f["ms"] for f in fam.values())
+    top = max((o for o in ops if o["kind"] == "gemm"), key=lambda o: o["flops"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f).get("gemm_dram_bytes_per_launch")
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"batch={B} per GPU, VQA head, {V} regions x {Tin} tokens (BASELINE.json configs[1]), "
-                                   f"bf16 operands / fp32 accumulate; random-init 268M-param ViLBERT (seed 42)",
+                                   f"{args.dtype} tensor-core operands / fp32 accumulate (tcgen05 kind::f16, same rate as bf16); "
+                                   f"random-init 268M-param ViLBERT (seed 42)",
                        "global_batch": B * world, "per_gpu_batch": B, "n_tokens": Tin, "n_regions": V,
                        "parallelism": f"dp{world} (batch sharding, no collective)",
                        "l2": f"inputs rotate over {args.rotate} resident batches ({args.rotate * in_bytes / 1e6:.0f} MB) "
                              f"+ {model._dims['weight_bytes'] / 1e6:.0f} MB of weights > 126 MB L2",
-                       "cuda_graph": not args.no_graph, "pdl": bool(args.pdl),
+                       "cuda_graph": not args.no_graph, "pdl": bool(args.pdl), "layernorm": "fused" if args.fused_ln else "split",
                        "heads": "task heads" if args.all_heads else "vil_prediction"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(n_launch) * args.steps,
             "launches_per_step": int(n_launch),
-            "roofline": {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": tflops / pk["bf16_sustained"], "traffic": None,
-                         "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the step; 97% of FLOPs)",
+            "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": gemm_tflops / pk["bf16_sustained"], "traffic": traffic,
+                         "kernel": "gemm_persistent_kernel (tcgen05): all %d GEMM launches of one step, algorithmic 2MNK FLOPs / "
+                                   "CUDA-event time per launch" % g["launches"],
+                         "avg_launch_us": 1e3 * g["ms"] / g["launches"],
+                         "largest_gemm": {"M": top["dims"][0], "N": top["dims"][1], "K": top["dims"][2], "us": 1e3 * top["ms"],
+                                          "tflops": top["flops"] / (top["ms"] * 1e-3) / 1e12},
+                         "share_of_step": g["ms"] / serial_ms,
+                         "families_ms": {k: round(v["ms"], 4) for k, v in fam.items()},
+                         "whole_step_tflops": tflops, "whole_step_frac": tflops / pk["bf16_sustained"],
                          "flops_per_step": flops, "peak_source": pk["src"] + " (sustained cuBLAS bf16)"},
             "clocks": sampler.result()}
 
@@ -266,9 +297,9 @@ def run_b200(args):
         times = time_oracle(model_cpu, reqs[0], nb, 1)
         v = B * len(times) / sum(times)
         import torch as _t
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": CPU_THREADS, "kind": "port",
                                 "sample": f"{nb} forwards of batch {B} after 1 warm-up (torch fp32 oracle, "
-                                          f"{_t.get_num_threads()} threads, all heads + pre-training heads)"}
+                                          f"{_t.get_num_threads()} threads of {os.cpu_count()} vCPUs, all heads + pre-training heads)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     model.close()

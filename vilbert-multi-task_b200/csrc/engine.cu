@@ -887,6 +887,38 @@ struct vb200_engine {
             CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
         }
     }
+    // Per-op device time with CUDA events (eager, single stream: no overlap, every op bracketed by an event pair on the
+    // launching stream).  Used by bench.py for the per-kernel roofline; the workspace must hold a previous forward's data.
+    void profile_ops(Plan& pl, int iters, std::vector<double>& ms_out) {
+        cudaStream_t st;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        const size_t n = pl.ops.size();
+        std::vector<cudaEvent_t> ev(n + 1);
+        for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        ms_out.assign(n, 0.0);
+        try {
+            for (int it = 0; it < iters + 1; ++it) {            // first pass is a warm-up
+                CUDA_CHECK(cudaEventRecord(ev[0], st));
+                for (size_t i = 0; i < n; ++i) {
+                    launch_op(pl.ops[i], st);
+                    CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
+                }
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                if (it == 0) continue;
+                for (size_t i = 0; i < n; ++i) {
+                    float ms = 0.0f;
+                    CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                    ms_out[i] += ms / iters;
+                }
+            }
+        } catch (...) {
+            for (auto& e : ev) cudaEventDestroy(e);
+            cudaStreamDestroy(st);
+            throw;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        cudaStreamDestroy(st);
+    }
     void capture(Plan& pl) {
         cudaStream_t cs;
         CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -1076,6 +1108,31 @@ int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_r
         Plan* pl = h->get_plan(batch, n_tokens, n_regions, select & VB200_OUT_ALL);
         if (n_launches) *n_launches = static_cast<int64_t>(pl->ops.size()) + 2;   // + text-embed + image-pack
         if (flops) *flops = pl->flops;
+    });
+}
+
+int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select, int32_t iters,
+                      int32_t max_ops, int32_t* n_ops, int32_t* kinds, double* ms, double* flops, int32_t* dims) {
+    if (h == nullptr || n_ops == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        CUDA_CHECK(cudaSetDevice(h->opt.device));
+        Plan* pl = h->get_plan(batch, n_tokens, n_regions, select & VB200_OUT_ALL);
+        std::vector<double> t;
+        h->profile_ops(*pl, iters < 1 ? 1 : iters, t);
+        const int n = static_cast<int>(pl->ops.size());
+        *n_ops = n;
+        for (int i = 0; i < n && i < max_ops; ++i) {
+            const Op& op = pl->ops[i];
+            if (kinds) kinds[i] = static_cast<int>(op.kind);
+            if (ms) ms[i] = t[i];
+            if (flops) flops[i] = op.flops;
+            if (dims) {
+                dims[4 * i + 0] = op.kind == Op::GEMM ? op.ep.M : (op.kind == Op::LAYERNORM ? op.ln_M : op.B);
+                dims[4 * i + 1] = op.kind == Op::GEMM ? op.ep.N : (op.kind == Op::LAYERNORM ? op.ln_N : op.La);
+                dims[4 * i + 2] = op.kind == Op::GEMM ? op.ep.K : op.Lb;
+                dims[4 * i + 3] = op.kind == Op::GEMM ? (op.ep.act | (op.ln ? 16 : 0)) : op.heads;
+            }
+        }
     });
 }
 

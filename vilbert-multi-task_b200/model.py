@@ -185,6 +185,20 @@ class VILBertForVLTasks(object):
                 self._handle)
         return n.value, f.value
 
+    def profile_ops(self, batch, n_tokens, n_regions, select=L.OUT_TASK_HEADS, iters=5):
+        """Per-launch device times (ms) of one forward, CUDA events around every kernel (eager, one stream)."""
+        cap = 2048
+        n = C.c_int32()
+        kinds = (C.c_int32 * cap)()
+        ms = (C.c_double * cap)()
+        fl = (C.c_double * cap)()
+        dims = (C.c_int32 * (4 * cap))()
+        L.check(L.load().vb200_profile_ops(self._handle, batch, n_tokens, n_regions, select, iters, cap, C.byref(n), kinds, ms,
+                                           fl, dims), self._handle)
+        names = {0: "gemm", 1: "self_attention", 2: "co_attention", 3: "rowdot", 4: "layernorm"}
+        return [dict(kind=names.get(kinds[i], "?"), ms=ms[i], flops=fl[i], dims=list(dims[4 * i:4 * i + 4]))
+                for i in range(min(n.value, cap))]
+
     def _prep(self, question, features, spatials, segment_ids, input_mask, image_mask, task_tokens, device):
         def dev(t, dtype):
             if not torch.is_tensor(t):
