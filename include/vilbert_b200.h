@@ -143,7 +143,7 @@ int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_r
                     int64_t* n_launches, double* flops);
 int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
 /* Per-launch device time of one forward of this shape (after at least one vb200_forward of it): every kernel of the plan is
- * launched eagerly on one stream between two CUDA events, `iters` times after a warm-up pass.  kinds: 0 GEMM, 1 self-attention,
+ * captured 8x into its own CUDA graph and replayed `iters` times between two CUDA events (no host launch gaps).  kinds: 0 GEMM, 1 self-attention,
  * 2 co-attention, 3 narrow head, 4 LayerNorm; dims[4*i..] = {M, N, K, act|16*fusedLN} for GEMMs.  Profiling aid for bench.py. */
 int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select, int32_t iters,
                       int32_t max_ops, int32_t* n_ops, int32_t* kinds, double* ms, double* flops, int32_t* dims);

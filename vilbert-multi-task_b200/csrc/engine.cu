@@ -887,37 +887,45 @@ struct vb200_engine {
             CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
         }
     }
-    // Per-op device time with CUDA events (eager, single stream: no overlap, every op bracketed by an event pair on the
-    // launching stream).  Used by bench.py for the per-kernel roofline; the workspace must hold a previous forward's data.
+    // Per-op device time: each launch-list entry is captured `kRep` times into its own CUDA graph and the graph replayed
+    // between two CUDA events on the launching stream, so the number is the kernel's duration (incl. the grid launch
+    // latency every launch pays inside the captured forward as well) without host launch gaps.  Every op is idempotent on
+    // the plan's workspace, which must hold a previous forward's data.  Used by bench.py for the per-kernel roofline.
     void profile_ops(Plan& pl, int iters, std::vector<double>& ms_out) {
+        constexpr int kRep = 8;
         cudaStream_t st;
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
         const size_t n = pl.ops.size();
-        std::vector<cudaEvent_t> ev(n + 1);
-        for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
         ms_out.assign(n, 0.0);
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
         try {
-            for (int it = 0; it < iters + 1; ++it) {            // first pass is a warm-up
-                CUDA_CHECK(cudaEventRecord(ev[0], st));
-                for (size_t i = 0; i < n; ++i) {
-                    launch_op(pl.ops[i], st);
-                    CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
-                }
+            for (size_t i = 0; i < n; ++i) {
+                CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                for (int r = 0; r < kRep; ++r) launch_op(pl.ops[i], st);
+                CUDA_CHECK(cudaStreamEndCapture(st, &g));
+                CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+                CUDA_CHECK(cudaGraphLaunch(ge, st));                    // warm-up
+                CUDA_CHECK(cudaEventRecord(e0, st));
+                for (int it = 0; it < iters; ++it) CUDA_CHECK(cudaGraphLaunch(ge, st));
+                CUDA_CHECK(cudaEventRecord(e1, st));
                 CUDA_CHECK(cudaStreamSynchronize(st));
-                if (it == 0) continue;
-                for (size_t i = 0; i < n; ++i) {
-                    float ms = 0.0f;
-                    CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-                    ms_out[i] += ms / iters;
-                }
+                float ms = 0.0f;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+                ms_out[i] = ms / (static_cast<double>(iters) * kRep);
+                cudaGraphExecDestroy(ge); ge = nullptr;
+                cudaGraphDestroy(g); g = nullptr;
             }
         } catch (...) {
-            for (auto& e : ev) cudaEventDestroy(e);
-            cudaStreamDestroy(st);
+            if (ge) cudaGraphExecDestroy(ge);
+            if (g) cudaGraphDestroy(g);
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
             throw;
         }
-        for (auto& e : ev) cudaEventDestroy(e);
-        cudaStreamDestroy(st);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     }
     void capture(Plan& pl) {
         cudaStream_t cs;
