@@ -1,0 +1,104 @@
+"""BASELINE.json configs 2-3 as parity cases (reduced sizes) plus the worker-level decode on the GPU engine. `-m gpu`.
+
+* multi-task batch (VQA + NLVR2 + RefCOCO in thirds), sharded on pair-aligned boundaries: per-shard outputs equal the
+  un-sharded ones bit for bit, and match the oracle;
+* caption-image retrieval score matrix through vilbert_b200.parallel (single process = world 1) vs the oracle;
+* prediction() top-k dicts from engine logits == the same decode applied to oracle logits.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(full_oracle):
+    import vilbert_b200 as vb
+    cfg = vb.BertConfig.from_dict(full_oracle.config.to_dict())
+    m = vb.VILBertForVLTasks.from_pretrained(full_oracle.state_dict(), config=cfg, num_labels=full_oracle.num_labels).eval().cuda(0)
+    yield m
+    m.close()
+
+
+def test_multitask_batch_sharded(full_oracle, engine, parity_log):
+    """configs[2] at B=24: task tokens 1 (VQA) / 12 (NLVR2, adjacent pairs) / 11 (RefCOCO) in thirds; 3 pair-aligned shards."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import parallel as P
+    B = 24
+    inp = list(R.make_inputs(B, 30, 36, seed=555, pad_regions=2))
+    task = torch.cat([torch.full((8, 1), 1), torch.full((8, 1), 12), torch.full((8, 1), 11)]).long()
+    inp[7] = task
+    ref = full_oracle(*inp, compute_pretraining_heads=False)
+    dev = [t.cuda() for t in inp]
+    whole = engine(*dev)
+    torch.cuda.synchronize()
+    for i, name in ((0, "vil_prediction"), (3, "vil_binary_prediction"), (6, "vision_logit")):
+        r, o = ref[i], whole[i].cpu()
+        small = r.abs() < 1000
+        err = float((o - r).abs()[small].max())
+        parity_log(test="multitask_B24", output=name, max_abs_err=err)
+        assert err < 1e-2, (name, err)
+    world = 3
+    outs = []
+    for rank in range(world):
+        lo, hi = P.shard_range(B, rank, world, pair_aligned=True)
+        assert lo % 2 == 0 and hi % 2 == 0
+        outs.append(engine(*[t[lo:hi] for t in dev]))
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([o[0] for o in outs]), whole[0])
+    assert torch.equal(torch.cat([o[3] for o in outs]), whole[3])          # NLVR2 pairs never straddle a shard
+    assert torch.equal(torch.cat([o[6] for o in outs]), whole[6])
+
+
+def test_retrieval_score_matrix(full_oracle, engine, parity_log):
+    """configs[3] at 6 captions x 5 images: score[c, i] = vil_logit of pair (c, i), task token 7 (worker.py:278-284, 359)."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import parallel as P
+    n_cap, n_img = 6, 5
+    cap = R.make_inputs(n_cap, 30, 36, seed=901)
+    img = R.make_inputs(n_img, 30, 36, seed=902)
+    q, seg, im = cap[0], cap[3], cap[4]
+    f, s, vm = img[1], img[2], img[5]
+    ref = torch.empty(n_cap, n_img)
+    for c in range(n_cap):
+        out = full_oracle(q[c:c + 1].repeat(n_img, 1), f, s, seg[c:c + 1].repeat(n_img, 1), im[c:c + 1].repeat(n_img, 1), vm,
+                          None, torch.full((n_img, 1), 7), compute_pretraining_heads=False)
+        ref[c] = out[2].view(-1)
+    score = P.make_pair_scorer(engine, (q.cuda(), seg.cuda(), im.cuda()), (f.cuda(), s.cuda(), vm.cuda()))
+    full = P.retrieval_scores(score, n_cap, n_img, image_chunk=3).cpu()
+    err = float((full - ref).abs().max())
+    parity_log(test="retrieval_6x5", max_abs_err=err, ref_std=float(ref.std()))
+    assert full.shape == (n_cap, n_img) and err < 1e-2
+    # ranking of the images per caption is what the worker returns (worker.py:359-366)
+    assert torch.equal(full.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("task_id,n_img", [("1", 1), ("15", 1), ("12", 2), ("13", 1), ("7", 3), ("11", 1)])
+def test_prediction_on_engine_matches_oracle_decode(full_oracle, engine, task_id, n_img):
+    """worker.prediction() driven by the engine returns the dict the same decode gives on the oracle's logits."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import worker_api as W
+    W.model = engine
+    inp = R.make_inputs(n_img, 37, 20, seed=77 + n_img)
+    text, segs, mask = inp[0][:1], inp[3][:1], inp[4][:1]
+    task = torch.tensor([[int(task_id)]])
+    infos = [{"image_width": 640, "image_height": 480}] * n_img
+    ans = W.prediction(text.cuda(), inp[1].cuda(), inp[2].cuda(), segs.cuda(), mask.cuda(), inp[5].cuda(), inp[6].cuda(),
+                       task.cuda(), task_id, infos)
+
+    class OracleAsModel:
+        _device = 0
+
+        def __call__(self, *a, **kw):
+            kw.pop("select", None)
+            a = [t.cpu() if torch.is_tensor(t) else t for t in a]
+            return full_oracle(*a, compute_pretraining_heads=False)
+    W.model = OracleAsModel()
+    ref = W.prediction(text, inp[1], inp[2], segs, mask, inp[5], inp[6], task, task_id, infos)
+    W.model = engine
+    if isinstance(ans, list):
+        assert [(a["x1"], a["y1"], a["x2"], a["y2"]) for a in ans] == [(a["x1"], a["y1"], a["x2"], a["y2"]) for a in ref]
+        assert [a["confidence"] for a in ans] == pytest.approx([a["confidence"] for a in ref], abs=0.5)
+    else:
+        assert ans["top3_answer"] == ref["top3_answer"]
+        assert ans["top3_confidence"] == pytest.approx(ref["top3_confidence"], abs=5e-3)
