@@ -25,7 +25,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 
-template <int BLOCK_N, bool LN>
+// EPI8: eight epilogue warps (two column groups per TMEM lane quarter).  LayerNorm tiles, GELU tiles (the erf costs ~16
+// instructions per element: with four warps the epilogue of a 128x128 tile took 11 k cycles, 3.5x its MMA time) and 256-wide tiles.
+template <int BLOCK_N, bool LN, bool EPI8 = LN>
 struct PCfg {
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
@@ -35,14 +37,16 @@ struct PCfg {
     // an SM needs ~6 stages in flight to be MMA-bound.  Plain tiles: 3 stages x 2 CTAs per SM (the second CTA also lets a
     // kernel of the other ViLBERT stream share the SM).  LayerNorm tiles run one CTA per SM (clusters, 8 epilogue warps
     // with the row slice in registers) and take the whole ring themselves.
-    static constexpr int kEpiWarps = LN ? 8 : 4;
+    static constexpr int kEpiWarps = (LN || EPI8) ? 8 : 4;
     static constexpr int kEpiThreads = 32 * kEpiWarps;
     static constexpr int kThreads = 64 + kEpiThreads;            // warp 0 TMA, warp 1 MMA (+TMEM alloc), then epilogue
     static constexpr int kMinBlocks = (LN || BLOCK_N >= 192) ? 1 : 2;
     // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
     // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
     //   plain: 32 rows x 20 words of packed 16-bit pairs;  LN: 32 rows x 33 fp32 (serves the fp32 and the 16-bit output)
-    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 32 * 20 * 4;
+    //   plain, 8 warps, two CTAs per SM: only 32 x 12 words fit (16-bit outputs, 16 columns at a time; fp32 falls back to
+    //   per-lane stores -- that combination only occurs for the 64-row classifier heads)
+    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : ((EPI8 && BLOCK_N < 192) ? 32 * 12 * 4 : 32 * 20 * 4);
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
     static constexpr int kStages = kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit);
@@ -211,6 +215,34 @@ __device__ __forceinline__ void store16_coalesced(uint32_t* st, __nv_bfloat16* o
     }
     __syncwarp();                                          // staging buffer is reused by the next chunk
 }
+// Same, 16 columns at a time through a 32 x 12-word buffer (the 8-warp plain epilogue has only that much shared memory):
+// every store instruction writes 16 rows x 32 contiguous bytes (one full sector per row).
+template <bool F16>
+__device__ __forceinline__ void store16_coalesced_h(uint32_t* st, __nv_bfloat16* out, int ld, int m_warp, int M, int ncol,
+                                                    const float (&v)[32], int lane) {
+    constexpr int S = 12;
+    const int piece = lane & 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint4 u;
+            u.x = F16 ? pack16x2_rt(v[16 * h + 8 * j + 0], v[16 * h + 8 * j + 1], 1) : pack_bf16x2(v[16 * h + 8 * j + 0], v[16 * h + 8 * j + 1]);
+            u.y = F16 ? pack16x2_rt(v[16 * h + 8 * j + 2], v[16 * h + 8 * j + 3], 1) : pack_bf16x2(v[16 * h + 8 * j + 2], v[16 * h + 8 * j + 3]);
+            u.z = F16 ? pack16x2_rt(v[16 * h + 8 * j + 4], v[16 * h + 8 * j + 5], 1) : pack_bf16x2(v[16 * h + 8 * j + 4], v[16 * h + 8 * j + 5]);
+            u.w = F16 ? pack16x2_rt(v[16 * h + 8 * j + 6], v[16 * h + 8 * j + 7], 1) : pack_bf16x2(v[16 * h + 8 * j + 6], v[16 * h + 8 * j + 7]);
+            *reinterpret_cast<uint4*>(st + lane * S + 4 * j) = u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int r = it * 16 + (lane >> 1);
+            const uint4 u = *reinterpret_cast<const uint4*>(st + r * S + 4 * piece);
+            if (m_warp + r < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(m_warp + r) * ld + ncol + 16 * h + piece * 8) = u;
+        }
+        __syncwarp();
+    }
+}
 // fp32 output of one 32x32 chunk (row-per-lane in v) through a [32][17] fp32 transpose buffer, 16 columns at a time:
 // every store instruction writes 8 rows x 64 contiguous bytes (two full sectors per row).
 __device__ __forceinline__ void store_f32_coalesced(float* st, float* out, int ld, int m_warp, int M, int ncol,
@@ -268,11 +300,14 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
     __syncwarp();
 }
 
+template <int BLOCK_N, bool LN, int ACT>
+struct KCfg { using type = PCfg<BLOCK_N, LN, (LN || ACT == kActGelu || BLOCK_N >= 256)>; };
+
 template <int BLOCK_N, bool LN, int ACT, bool F16>
-__global__ void __launch_bounds__(PCfg<BLOCK_N, LN>::kThreads, PCfg<BLOCK_N, LN>::kMinBlocks)
+__global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT>::type::kThreads, KCfg<BLOCK_N, LN, ACT>::type::kMinBlocks)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const GemmEpilogue p, const int num_m_tiles, const int num_n_tiles) {
-    using Cfg = PCfg<BLOCK_N, LN>;
+    using Cfg = typename KCfg<BLOCK_N, LN, ACT>::type;
     constexpr int kStages = Cfg::kStages;
     constexpr int kNC = Cfg::kNumChunks;
     constexpr int kEpiThreads = Cfg::kEpiThreads;
@@ -429,34 +464,61 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (stamp) stamps[4] = clock64();
-                float va[32], vb[32];
-                tmem_ld32_issue(taddr, va);
-#pragma unroll
-                for (int c = 0; c < kNC; ++c) {
-                    float (&v)[32] = (c & 1) ? vb : va;
-                    float (&vn)[32] = (c & 1) ? va : vb;
-                    const int nc = n0 + c * 32;
-                    tmem_ld_wait();                                               // chunk c is in registers
-                    if (c + 1 < kNC) {
-                        tmem_ld32_issue(taddr + (c + 1) * 32, vn);               // chunk c+1 streams in behind the math
-                    } else {
-                        tc_fence_before();
-                        mbar_arrive(&tmem_empty_bar[acc]);                        // every TMEM read of this tile has completed:
-                    }                                                             // accumulator free for tile it+2
-                    bias_act32<ACT>(v, bias_t + c * 32);
+                auto finish_chunk = [&](float (&v)[32], int nc) {
+                    bias_act32<ACT>(v, bias_t + (nc - n0));
                     if (p.mul != nullptr && m_ok) {
                         const float* mp = p.mul + static_cast<size_t>(m) * p.ld_mul + nc;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
                     }
-                    if (st_fast && nc + 32 <= p.N) {                // warp-uniform: row-contiguous stores via the transpose buffer
-                        uint8_t* xb = s_xpose + ew * Cfg::kXposeBytesPerWarp;
-                        if (p.out_f32 != nullptr)
-                            store_f32_coalesced(reinterpret_cast<float*>(xb), p.out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
-                        if (p.out_bf16 != nullptr)
-                            store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
-                    } else if (m_ok) {
-                        store_chunk<F16>(p, m, nc, false, v);
+                    uint8_t* xb = s_xpose + ew * Cfg::kXposeBytesPerWarp;
+                    constexpr bool kBigBuf = Cfg::kXposeBytesPerWarp >= 32 * 20 * 4;
+                    const bool fast16 = st_fast && nc + 32 <= p.N && p.out_bf16 != nullptr;
+                    const bool fast32 = st_fast && nc + 32 <= p.N && p.out_f32 != nullptr && kBigBuf;   // all warp-uniform
+                    if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), p.out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
+                    if (fast16) {
+                        if constexpr (kBigBuf) store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
+                        else store16_coalesced_h<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
+                    }
+                    if (m_ok && ((p.out_f32 != nullptr && !fast32) || (p.out_bf16 != nullptr && !fast16))) {
+                        GemmEpilogue ps = p;                       // per-lane (ragged N / odd stride / small buffer) remainder
+                        if (fast32) ps.out_f32 = nullptr;
+                        if (fast16) ps.out_bf16 = nullptr;
+                        store_chunk<F16>(ps, m, nc, false, v);
+                    }
+                };
+                if constexpr (Cfg::kEpiWarps == 4) {
+                    float va[32], vb[32];
+                    tmem_ld32_issue(taddr, va);
+#pragma unroll
+                    for (int c = 0; c < kNC; ++c) {
+                        float (&v)[32] = (c & 1) ? vb : va;
+                        float (&vn)[32] = (c & 1) ? va : vb;
+                        tmem_ld_wait();                                           // chunk c is in registers
+                        if (c + 1 < kNC) {
+                            tmem_ld32_issue(taddr + (c + 1) * 32, vn);           // chunk c+1 streams in behind the math
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(&tmem_empty_bar[acc]);                    // every TMEM read of this tile has completed:
+                        }                                                         // accumulator free for tile it+2
+                        finish_chunk(v, n0 + c * 32);
+                    }
+                } else {
+                    // eight warps: column group g = ew / 4 takes chunks [g * kNC/2, (g+1) * kNC/2); thread-level parallelism
+                    // hides the TMEM latency, one chunk in registers at a time keeps two CTAs per SM within 102 registers
+                    constexpr int kCPG = kNC / 2;
+                    const int g = ew >> 2;
+#pragma unroll
+                    for (int ci = 0; ci < kCPG; ++ci) {
+                        const int c = g * kCPG + ci;
+                        float v[32];
+                        tmem_ld32_issue(taddr + c * 32, v);
+                        tmem_ld_wait();
+                        if (ci + 1 == kCPG) {
+                            tc_fence_before();
+                            mbar_arrive(&tmem_empty_bar[acc]);
+                        }
+                        finish_chunk(v, n0 + c * 32);
                     }
                 }
                 if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
@@ -586,9 +648,8 @@ inline int num_sms() {
     return n;
 }
 
-template <int BLOCK_N, bool LN>
+template <typename Cfg, bool LN>
 void fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, dim3 grid, int cluster, int pdl, cudaStream_t st) {
-    using Cfg = PCfg<BLOCK_N, LN>;
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
@@ -614,7 +675,7 @@ void fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, dim3 grid, in
 // resident: LN only -- how many clusters of this size can be co-resident (grid.y is capped to it)
 template <int BLOCK_N, bool LN, int ACT, bool F16>
 cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int resident, cudaStream_t st) {
-    using Cfg = PCfg<BLOCK_N, LN>;
+    using Cfg = typename KCfg<BLOCK_N, LN, ACT>::type;
     auto kern = gemm_persistent_kernel<BLOCK_N, LN, ACT, F16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -631,7 +692,7 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
-    fill_cfg<BLOCK_N, LN>(cfg, attrs, grid, cluster, ep.pdl, st);
+    fill_cfg<Cfg, LN>(cfg, attrs, grid, cluster, ep.pdl, st);
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, m_tiles, n_tiles);
 }
 

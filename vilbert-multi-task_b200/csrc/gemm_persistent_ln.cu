@@ -16,7 +16,7 @@ static int max_clusters(int cluster) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) == cudaSuccess) {
         cudaLaunchConfig_t cfg;
         cudaLaunchAttribute attrs[2];
-        fill_cfg<BLOCK_N, true>(cfg, attrs, dim3(cluster, 1, 1), cluster, 0, nullptr);
+        fill_cfg<Cfg, true>(cfg, attrs, dim3(cluster, 1, 1), cluster, 0, nullptr);
         if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
     }
     cudaGetLastError();
