@@ -10,8 +10,8 @@
 // 16 B so ldmatrix is conflict-free); each warp owns 16 query rows and runs a register-resident flash-attention
 // pass over the keys in blocks of 64: S = Q K^T on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32
 // accumulate), additive key mask, online softmax with quad shuffles in fp32, P V again on mma.sync.
-// The co-attention kernel stages the six operand tiles of a (sample, head) once and produces BOTH directions
-// (text-query x image-key -> text context, image-query x text-key -> image context) from them.
+// The co-attention kernel produces BOTH directions of a (sample, head) in one launch (text-query x image-key -> text
+// context, then image-query x text-key -> image context), re-using one Q/K/V buffer set so five CTAs fit per SM.
 #include "kernels.h"
 
 namespace vb {
@@ -206,17 +206,19 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
                     int hidden, const float* __restrict__ img_mask_add, const float* __restrict__ txt_mask_add,
                     uint16_t* __restrict__ ctx_txt, int ld_ctx_txt, uint16_t* __restrict__ ctx_img, int ld_ctx_img, int T,
                     int V, float scale_l2, int pdl) {
+    // Two phases over ONE set of Q/K/V buffers sized for the longer sequence (39 KB at T=31/V=36 instead of 65 KB for all
+    // six tiles: 5 CTAs per SM, so the 512 (sample, head) CTAs of a batch-64 layer are resident in a single wave).
+    //   phase 1: text queries (Q2) over image keys/values (K1, V1) -> context for the text stream
+    //   phase 2: image queries (Q1) over text keys/values (K2, V2)  -> context for the image stream
     extern __shared__ __align__(16) uint8_t smem_attn[];
     constexpr int kStride = AttnTile<D>::kStride;
     const int h = blockIdx.x, b = blockIdx.y;
     const int Tp = pad16(T), Vp = pad16(V);
-    uint16_t* Q1 = reinterpret_cast<uint16_t*>(smem_attn);   // image side: V rows
-    uint16_t* K1 = Q1 + Vp * kStride;
-    uint16_t* V1 = K1 + Vp * kStride;
-    uint16_t* Q2 = V1 + Vp * kStride;                        // text side: T rows
-    uint16_t* K2 = Q2 + Tp * kStride;
-    uint16_t* V2 = K2 + Tp * kStride;
-    float* mask_img = reinterpret_cast<float*>(V2 + Tp * kStride);
+    const int Lp = Tp > Vp ? Tp : Vp;
+    uint16_t* Qs = reinterpret_cast<uint16_t*>(smem_attn);
+    uint16_t* Ks = Qs + Lp * kStride;
+    uint16_t* Vs = Ks + Lp * kStride;
+    float* mask_img = reinterpret_cast<float*>(Vs + Lp * kStride);
     float* mask_txt = mask_img + V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
@@ -224,25 +226,25 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
 
     const uint16_t* bi = qkv_img + static_cast<size_t>(b) * V * ld_img + h * D;
     const uint16_t* bt = qkv_txt + static_cast<size_t>(b) * T * ld_txt + h * D;
-    load_tile<D>(Q1, bi, V, Vp, ld_img);
-    load_tile<D>(K1, bi + hidden, V, Vp, ld_img);
-    load_tile<D>(V1, bi + 2 * hidden, V, Vp, ld_img);
-    load_tile<D>(Q2, bt, T, Tp, ld_txt);
-    load_tile<D>(K2, bt + hidden, T, Tp, ld_txt);
-    load_tile<D>(V2, bt + 2 * hidden, T, Tp, ld_txt);
+    load_tile<D>(Qs, bt, T, Tp, ld_txt);                         // Q2
+    load_tile<D>(Ks, bi + hidden, V, Vp, ld_img);                // K1
+    load_tile<D>(Vs, bi + 2 * hidden, V, Vp, ld_img);            // V1
     for (int j = threadIdx.x; j < V; j += blockDim.x) mask_img[j] = img_mask_add[b * V + j] * kLog2e;
     for (int j = threadIdx.x; j < T; j += blockDim.x) mask_txt[j] = txt_mask_add[b * T + j] * kLog2e;
     cp_async_wait_all();
     __syncthreads();
     uint16_t* out_t = ctx_txt + static_cast<size_t>(b) * T * ld_ctx_txt + h * D;
+    for (int t = warp; t * 16 < T; t += nwarps)
+        attend_tile<D, F16>(Qs, Ks, Vs, t * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane);
+    __syncthreads();                                             // everyone is done reading phase-1 tiles
+    load_tile<D>(Qs, bi, V, Vp, ld_img);                         // Q1
+    load_tile<D>(Ks, bt + hidden, T, Tp, ld_txt);                // K2
+    load_tile<D>(Vs, bt + 2 * hidden, T, Tp, ld_txt);            // V2
+    cp_async_wait_all();
+    __syncthreads();
     uint16_t* out_v = ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D;
-    const int tt = Tp / 16, tv = Vp / 16;
-    for (int t = warp; t < tt + tv; t += nwarps) {
-        if (t < tt)   // text queries over image keys/values -> context for the text stream
-            attend_tile<D, F16>(Q2, K1, V1, t * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane);
-        else          // image queries over text keys/values -> context for the image stream
-            attend_tile<D, F16>(Q1, K2, V2, (t - tt) * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane);
-    }
+    for (int t = warp; t * 16 < V; t += nwarps)
+        attend_tile<D, F16>(Qs, Ks, Vs, t * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane);
 }
 
 template <int D, bool F16>
@@ -253,7 +255,7 @@ static cudaError_t launch_self(const __nv_bfloat16* qkv, int ld_qkv, int hidden,
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = set_smem(self_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    const int nwarps = min(8, Lp / 16);
+    const int nwarps = max(4, min(8, Lp / 16));               // >= 4 warps so the cp.async staging is spread over 128 threads
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv), ld_qkv, hidden, key_mask_add, reinterpret_cast<uint16_t*>(ctx),
@@ -278,11 +280,12 @@ static cudaError_t launch_co(const __nv_bfloat16* qkv_img, int ld_img, const __n
                              __nv_bfloat16* ctx_img, int ld_ctx_img, int B, int T, int V, int heads, int pdl,
                              cudaStream_t st) {
     const int Tp = pad16(T), Vp = pad16(V);
-    const size_t smem = 3 * AttnTile<D>::bytes(Tp + Vp) + sizeof(float) * (T + V);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;     // T + V too long for one CTA's shared memory
+    const int Lp = Tp > Vp ? Tp : Vp;
+    const size_t smem = 3 * AttnTile<D>::bytes(Lp) + sizeof(float) * (T + V);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;     // sequence too long for one CTA's shared memory
     cudaError_t e = set_smem(co_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    const int nwarps = min(8, (Tp + Vp) / 16);
+    const int nwarps = max(4, min(8, Lp / 16));               // >= 4 warps so the cp.async staging is spread over 128 threads
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv_img), ld_img, reinterpret_cast<const uint16_t*>(qkv_txt), ld_txt,

@@ -322,6 +322,8 @@ struct Op {
     double flops = 0;
 };
 
+constexpr int kMaxSplitK = 3;   // fp32 partial-sum buffers of the split-K GEMMs that feed the row LayerNorm kernel
+
 struct OutBuf { float* p = nullptr; int rows = 0, cols = 0, ld = 0; };
 
 struct Plan {
@@ -630,9 +632,20 @@ struct vb200_engine {
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = opt.use_pdl;
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
+        int split_k = 1;
         if (split_ln) {
             float* y = pl.y_scratch[stream];
             e.out_f32 = y; e.ld_f32 = W.N;
+            // Few tiles and a long K (FFN-out: K = 3072, 96 tiles at batch 64): cut K so ~2 CTAs per SM run short main loops;
+            // the LayerNorm kernel that follows sums the fp32 partials for free (it reads y anyway).
+            const long long tiles = ((a_rows + 127) / 128) * ((W.N + op.block_n - 1) / op.block_n);
+            const int num_kb = W.ldw / 64;
+            if (!gemm_v1 && act == vb::kActNone && num_kb >= 24 && tiles < 148) {
+                split_k = static_cast<int>(std::min<long long>(kMaxSplitK, std::max<long long>(1, 296 / tiles)));
+                while (split_k > 1 && num_kb / split_k < 6) --split_k;
+            }
+            e.split_k = split_k;
+            e.split_stride = static_cast<long long>(a_rows) * W.N;
         } else {
             e.res = res; e.ld_res = ld_res;
             e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr;
@@ -649,6 +662,7 @@ struct vb200_engine {
             l.ln_g = ln->g; l.ln_b = ln->b; l.ln_out_f = out_f; l.ln_out_h = out_b; l.ln_ld = W.N;
             l.ld_out = out_f ? ld_f : 0; l.ld_a = out_b ? ld_b : 0;
             l.ln_M = static_cast<int>(a_rows); l.ln_N = W.N;
+            l.n_out = split_k;                                  // number of fp32 partials to sum
             pl.ops.push_back(l);
         }
     }
@@ -691,8 +705,8 @@ struct vb200_engine {
         }
         if (!fused_ln) {
             const size_t n0 = std::max({static_cast<size_t>(Mt) * H, static_cast<size_t>(Mv) * Hv, static_cast<size_t>(B) * 2 * Hb});
-            pl.y_scratch[0] = pl.mem.alloc_n<float>(n0);
-            pl.y_scratch[1] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv);
+            pl.y_scratch[0] = pl.mem.alloc_n<float>(n0 * kMaxSplitK);
+            pl.y_scratch[1] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv * kMaxSplitK);
         }
         const int qt = 3 * std::max(H, Hb), qv = 3 * std::max(Hv, Hb);
         bf16* qkv_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * qt);
@@ -850,7 +864,8 @@ struct vb200_engine {
                                                    opt.use_pdl, opt.act_fp16, st));
                 break;
             case Op::LAYERNORM:
-                CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
+                CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.n_out > 1 ? op.n_out : 1, static_cast<long long>(op.ln_M) * op.ln_N,
+                                                  op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
                                                   op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, opt.use_pdl, st));
                 break;
             case Op::ROWDOT:
@@ -1193,7 +1208,7 @@ int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t
                     float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
                     int32_t act_fp16, void* cuda_stream) {
     return op_guard([&] {
-        CUDA_CHECK(vb::launch_ln_residual(y, (int)ld_y, residual, (int)ld_res, gamma, beta, eps, out_f32, (int)ld_f32,
+        CUDA_CHECK(vb::launch_ln_residual(y, (int)ld_y, 1, 0, residual, (int)ld_res, gamma, beta, eps, out_f32, (int)ld_f32,
                                           static_cast<bf16*>(out_16), (int)ld_16, (int)M, (int)N, act_fp16 ? 1 : 0, 0,
                                           static_cast<cudaStream_t>(cuda_stream)));
     });

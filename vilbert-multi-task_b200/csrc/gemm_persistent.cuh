@@ -345,7 +345,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     // ---- tile assignment.  Non-LN: CTA b takes tiles b, b+grid, ... with the N index fastest (CTAs that run together
     // share an A row-panel in L2).  LN: gridDim.x = cluster size = num_n_tiles, blockIdx.y = cluster id; cluster c takes
     // M tiles c, c + gridDim.y, ... and the CTA's rank in the cluster is its (fixed) N tile.
-    const int total_tiles = LN ? num_m_tiles : num_m_tiles * num_n_tiles;
+    // split-K (plain kernel): tile index = (m * num_n_tiles + n) * split_k + s; slice s covers k-blocks [s * kbs, min(., num_kb))
+    const int split_k = LN ? 1 : (p.split_k > 1 ? p.split_k : 1);
+    const int kbs = (num_kb + split_k - 1) / split_k;
+    const int total_tiles = LN ? num_m_tiles : num_m_tiles * num_n_tiles * split_k;
     const int first_tile = LN ? static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.x);
     const int tile_stride = LN ? static_cast<int>(gridDim.y) : static_cast<int>(gridDim.x);
     const uint32_t cluster_size = LN ? cluster_nctarank() : 1u;
@@ -392,9 +395,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             int s = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-                const int m0 = (LN ? tile : tile / num_n_tiles) * kBlockM;
-                const int n0 = (LN ? static_cast<int>(my_rank) : tile % num_n_tiles) * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int mn = LN ? tile : tile / split_k;
+                const int ks = LN ? 0 : tile % split_k;
+                const int m0 = (LN ? tile : mn / num_n_tiles) * kBlockM;
+                const int n0 = (LN ? static_cast<int>(my_rank) : mn % num_n_tiles) * BLOCK_N;
+                const int kb_end = min(num_kb, (ks + 1) * kbs);
+                for (int kb = ks * kbs; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[s], phase ^ 1u);
                     uint8_t* sa = ring + s * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kStageBytesA;
@@ -418,16 +424,18 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int ks = LN ? 0 : tile % split_k;
+                const int kb_begin = ks * kbs, kb_end = min(num_kb, (ks + 1) * kbs);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[s], phase);
                     tc_fence_after();
-                    if (stamps && it == 0 && kb == 0) stamps[2] = clock64();
+                    if (stamps && it == 0 && kb == kb_begin) stamps[2] = clock64();
                     uint8_t* sa = ring + s * Cfg::kStageBytes;
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
                     const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                     umma_commit(&empty_bar[s]);
                     if (++s == kStages) { s = 0; phase ^= 1u; }
                 }
@@ -447,8 +455,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-            const int m0 = (LN ? tile : tile / num_n_tiles) * kBlockM;
-            const int n0 = (LN ? static_cast<int>(my_rank) : tile % num_n_tiles) * BLOCK_N;
+            const int mn = LN ? tile : tile / split_k;
+            const int ks = LN ? 0 : tile % split_k;
+            const int m0 = (LN ? tile : mn / num_n_tiles) * kBlockM;
+            const int n0 = (LN ? static_cast<int>(my_rank) : mn % num_n_tiles) * BLOCK_N;
             const int m = m0 + row;
             const bool m_ok = m < p.M;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
@@ -459,11 +469,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 float* bias_t = s_bias + acc * BLOCK_N;
                 // per-tile bias slice, double-buffered by accumulator parity; the named barrier also orders this tile's
                 // writes after every epilogue warp has finished the tile that last used the buffer
-                for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_t[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
+                for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_t[i] = (p.bias && ks == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
                 epi_bar_sync<kEpiThreads>();
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (stamp) stamps[4] = clock64();
+                float* const out_f32 = p.out_f32 ? p.out_f32 + static_cast<long long>(ks) * p.split_stride : nullptr;   // split-K slice
                 auto finish_chunk = [&](float (&v)[32], int nc) {
                     bias_act32<ACT>(v, bias_t + (nc - n0));
                     if (p.mul != nullptr && m_ok) {
@@ -475,13 +486,14 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     constexpr bool kBigBuf = Cfg::kXposeBytesPerWarp >= 32 * 20 * 4;
                     const bool fast16 = st_fast && nc + 32 <= p.N && p.out_bf16 != nullptr;
                     const bool fast32 = st_fast && nc + 32 <= p.N && p.out_f32 != nullptr && kBigBuf;   // all warp-uniform
-                    if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), p.out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
+                    if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
                     if (fast16) {
                         if constexpr (kBigBuf) store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                         else store16_coalesced_h<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                     }
                     if (m_ok && ((p.out_f32 != nullptr && !fast32) || (p.out_bf16 != nullptr && !fast16))) {
                         GemmEpilogue ps = p;                       // per-lane (ragged N / odd stride / small buffer) remainder
+                        ps.out_f32 = out_f32;
                         if (fast32) ps.out_f32 = nullptr;
                         if (fast16) ps.out_bf16 = nullptr;
                         store_chunk<F16>(ps, m, nc, false, v);
@@ -688,7 +700,7 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
         if (resident <= 0) return cudaErrorInvalidConfiguration;
         grid = dim3(cluster, std::min(m_tiles, resident), 1);
     } else {
-        grid = dim3(std::min(m_tiles * n_tiles, num_sms() * Cfg::kMinBlocks), 1, 1);
+        grid = dim3(std::min(m_tiles * n_tiles * (ep.split_k > 1 ? ep.split_k : 1), num_sms() * Cfg::kMinBlocks), 1, 1);
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];

@@ -18,6 +18,8 @@ static cudaError_t dispatch_plain(const CUtensorMap& ta, const CUtensorMap& tb, 
 cudaError_t launch_gemm_persistent_plain(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int block_n,
                                          cudaStream_t st) {
     if (ep.res != nullptr || ep.a_f16 != ep.out_f16) return cudaErrorInvalidValue;   // residual only with LayerNorm
+    if (ep.split_k > 1 && (ep.act != kActNone || ep.out_bf16 != nullptr || ep.mul != nullptr || ep.out_f32 == nullptr))
+        return cudaErrorInvalidValue;                                                 // split-K slices are raw fp32 partial sums
     switch (block_n) {
         case 64: return dispatch_plain<64>(ta, tb, ep, st);
         case 128: return dispatch_plain<128>(ta, tb, ep, st);

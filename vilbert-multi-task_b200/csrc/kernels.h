@@ -25,6 +25,8 @@ struct GemmEpilogue {
     int pdl;                      // launched with programmatic stream serialization
     int a_f16;                    // both GEMM operands (activations A, weights W) are fp16 instead of bf16
     int out_f16;                  // 16-bit output is fp16 instead of bf16
+    int split_k;                  // plain kernel only: K is cut into split_k slices, slice s writes its fp32 partial sum to
+    long long split_stride;       //   out_f32 + s * split_stride (bias added by slice 0); the row LayerNorm kernel sums them
     long long* timing;            // optional (profiling): 8 clock64 stamps per CTA, see gemm_persistent.cu; null in production
 };
 
@@ -53,9 +55,9 @@ cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const 
                                 int T, int V, int heads, int head_dim, int pdl, int f16, cudaStream_t st);
 
 // un-fused LayerNorm(y + res): fp32 stream out + 16-bit operand out (layernorm.cu)
-cudaError_t launch_ln_residual(const float* y, int ld_y, const float* res, int ld_res, const float* gamma, const float* beta,
-                               float eps, float* out_f32, int ld_f32, __nv_bfloat16* out16, int ld16, int M, int N, int f16,
-                               int pdl, cudaStream_t st);
+cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long long partial_stride, const float* res, int ld_res,
+                               const float* gamma, const float* beta, float eps, float* out_f32, int ld_f32,
+                               __nv_bfloat16* out16, int ld16, int M, int N, int f16, int pdl, cudaStream_t st);
 // K2: word + position + token-type gather, task-token row at index 1, LayerNorm; also builds the additive text mask.
 cudaError_t launch_text_embed(const int64_t* ids, const int64_t* seg, const int64_t* input_mask, const int64_t* task,
                               const float* word, const float* pos, const float* type, const float* task_tab,

@@ -15,7 +15,8 @@ constexpr int kLnMaxVec = 16;   // N <= 2048: float4 per lane per 128 columns
 
 template <bool F16>
 __global__ void __launch_bounds__(256)
-ln_residual_kernel(const float* __restrict__ y, int ld_y, const float* __restrict__ res, int ld_res,
+ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long long partial_stride,
+                   const float* __restrict__ res, int ld_res,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ out_f32, int ld_f32, uint16_t* __restrict__ out16, int ld16, int M, int N, int pdl) {
     if (pdl) { pdl_wait(); pdl_launch_dependents(); }
@@ -31,6 +32,10 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, const float* __restric
     for (int k = 0; k < kLnMaxVec; ++k) {
         if (k < nvec) {
             float4 a = yp[lane + 32 * k];
+            for (int sp = 1; sp < n_partials; ++sp) {          // split-K partial sums of the producing GEMM
+                const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(yp + lane + 32 * k) + sp * partial_stride);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
             if (rp) { const float4 r = rp[lane + 32 * k]; a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
             x[k] = a;
             s += a.x + a.y + a.z + a.w;
@@ -65,19 +70,19 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, const float* __restric
     }
 }
 
-cudaError_t launch_ln_residual(const float* y, int ld_y, const float* res, int ld_res, const float* gamma, const float* beta,
-                               float eps, float* out_f32, int ld_f32, __nv_bfloat16* out16, int ld16, int M, int N, int f16,
-                               int pdl, cudaStream_t st) {
+cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long long partial_stride, const float* res, int ld_res,
+                               const float* gamma, const float* beta, float eps, float* out_f32, int ld_f32,
+                               __nv_bfloat16* out16, int ld16, int M, int N, int f16, int pdl, cudaStream_t st) {
     if (N % 128 != 0 || N / 128 > kLnMaxVec || (ld_y & 3) || (res && (ld_res & 3)) || (out_f32 && (ld_f32 & 3)) ||
-        (out16 && (ld16 & 3)) || M < 1)
+        (out16 && (ld16 & 3)) || M < 1 || n_partials < 1 || (n_partials > 1 && (partial_stride & 3)))
         return cudaErrorInvalidValue;
     const dim3 grid((M + 7) / 8), block(256);
     uint16_t* o16 = reinterpret_cast<uint16_t*>(out16);
     if (f16)
-        return launch_ex(ln_residual_kernel<true>, grid, block, 0, pdl, st, y, ld_y, res, ld_res, gamma, beta, eps, out_f32,
-                         ld_f32, o16, ld16, M, N, pdl);
-    return launch_ex(ln_residual_kernel<false>, grid, block, 0, pdl, st, y, ld_y, res, ld_res, gamma, beta, eps, out_f32,
-                     ld_f32, o16, ld16, M, N, pdl);
+        return launch_ex(ln_residual_kernel<true>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, gamma,
+                         beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl);
+    return launch_ex(ln_residual_kernel<false>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, gamma,
+                     beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl);
 }
 
 }  // namespace vb
