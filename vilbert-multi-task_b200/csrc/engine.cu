@@ -362,6 +362,7 @@ struct vb200_engine {
     int num_labels = 0, gqa_labels = 0;
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
+    bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
     bool fused_ln = false;     // VB200_FUSED_LN=1: cluster-LayerNorm GEMM epilogue instead of GEMM(fp32) + row LayerNorm kernel
     Arena weights;
     std::string last_error;
@@ -640,7 +641,11 @@ struct vb200_engine {
             // the LayerNorm kernel that follows sums the fp32 partials for free (it reads y anyway).
             const long long tiles = ((a_rows + 127) / 128) * ((W.N + op.block_n - 1) / op.block_n);
             const int num_kb = W.ldw / 64;
-            if (!gemm_v1 && act == vb::kActNone && num_kb >= 24 && tiles < 148) {
+            // Measured at batch 64: the isolated FFN-out GEMM gets 1.7x faster, but the whole step gets 7 % SLOWER -- the 96-CTA
+            // kernel left SMs to the other ViLBERT stream's kernels, the 288-CTA split version does not -- and a split that
+            // depends on the tile count would make results depend on the batch size (sharding is bit-exact today).
+            // Kept behind VB200_SPLITK=1 for large-K / single-stream use.
+            if (split_k_enabled && !gemm_v1 && act == vb::kActNone && num_kb >= 24 && tiles < 148) {
                 split_k = static_cast<int>(std::min<long long>(kMaxSplitK, std::max<long long>(1, 296 / tiles)));
                 while (split_k > 1 && num_kb / split_k < 6) --split_k;
             }
@@ -1057,6 +1062,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         if (const char* v = getenv("VB200_GEMM")) eng->gemm_v1 = (strcmp(v, "v1") == 0);
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
+        if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
