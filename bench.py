@@ -44,6 +44,8 @@ def parse():
     p.add_argument("--all-heads", action="store_true", help="compute the seven task heads instead of VQA only")
     p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
                    help="16-bit format of the tensor-core operands (same tcgen05 rate; fp16 is the engine default, see DESIGN.md 2)")
+    p.add_argument("--inflight", type=int, default=2,
+                   help="batches in flight per GPU: steps alternate over this many CUDA streams / engine workspace slots")
     p.add_argument("--fused-ln", action="store_true", help="cluster-LayerNorm GEMM epilogue instead of GEMM + row LayerNorm")
     return p.parse_args()
 
@@ -188,8 +190,30 @@ def run_b200(args):
     dreqs = [[t.to(dev) for t in r] for r in reqs]
     in_bytes = sum(t.numel() * t.element_size() for i, t in enumerate(reqs[0]) if i != 6)
 
+    nfl = max(1, args.inflight if not args.no_graph else 1)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nfl)] if nfl > 1 else [torch.cuda.current_stream(dev)]
+
     def step(i):
-        return model(*dreqs[i % args.rotate], select=select)
+        # step i = one forward of one batch; consecutive steps go to alternating streams / workspace slots so that the
+        # kernels of one batch fill SMs the other leaves idle (every step still runs start to finish inside the timed region)
+        if nfl == 1:
+            return model(*dreqs[i % args.rotate], select=select)
+        with torch.cuda.stream(streams[i % nfl]):
+            return model(*dreqs[i % args.rotate], select=select, slot=i % nfl)
+
+    def fork():
+        if nfl > 1:
+            ev = torch.cuda.Event()
+            ev.record()
+            for s_ in streams:
+                s_.wait_event(ev)
+
+    def join():
+        if nfl > 1:
+            for s_ in streams:
+                ev = torch.cuda.Event()
+                ev.record(s_)
+                torch.cuda.current_stream(dev).wait_event(ev)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -197,15 +221,19 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for i in range(max(args.warmup, 3)):
+    fork()
+    for i in range(max(args.warmup, 3) * nfl):
         out = step(i)
+    join()
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork()
     for i in range(args.steps):
         out = step(i)
+    join()
     e1.record()
     sync_all()
     sampler.stop_flag = True
@@ -272,6 +300,7 @@ def run_b200(args):
                        "parallelism": f"dp{world} (batch sharding, no collective)",
                        "l2": f"inputs rotate over {args.rotate} resident batches ({args.rotate * in_bytes / 1e6:.0f} MB) "
                              f"+ {model._dims['weight_bytes'] / 1e6:.0f} MB of weights > 126 MB L2",
+                       "batches_in_flight": nfl,
                        "cuda_graph": not args.no_graph, "pdl": bool(args.pdl), "layernorm": "fused" if args.fused_ln else "split",
                        "heads": "task heads" if args.all_heads else "vil_prediction"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,

@@ -132,6 +132,12 @@ const char* vb200_last_error(vb200_handle h);
  * memory on the engine's device; enqueued on `cuda_stream` (a cudaStream_t passed as void*). */
 int vb200_forward(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, void* cuda_stream);
 
+/* Same with an explicit workspace slot (0..15): forwards on DIFFERENT slots may run concurrently on different streams (each
+ * slot owns its workspace, TMA descriptors and captured graph; weights are shared) -- how a server keeps more than one batch in
+ * flight so kernels of one batch fill the SMs another leaves idle.  vb200_forward is slot 0. */
+int vb200_forward_slot(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, int32_t slot,
+                       void* cuda_stream);
+
 /* Host-pointer forward: same, but every pointer is HOST memory (pinned for full speed); copies in, runs, copies
  * the selected outputs back and synchronises the stream before returning. */
 int vb200_forward_host(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select,

@@ -685,8 +685,10 @@ struct vb200_engine {
         return o;
     }
 
-    Plan* get_plan(int B, int Tin, int V, uint32_t select) {
-        std::vector<int64_t> key{B, Tin, V, static_cast<int64_t>(select)};
+    Plan* get_plan(int B, int Tin, int V, uint32_t select, int slot = 0) {
+        if (slot < 0 || slot > 15) fail(VB200_ERR_INVALID, "slot %d out of range (0..15)", slot);
+        if (slot > 0 && !opt.use_cuda_graph) fail(VB200_ERR_INVALID, "concurrent slots need CUDA-graph plans (use_cuda_graph)");
+        std::vector<int64_t> key{B, Tin, V, static_cast<int64_t>(select), slot};
         auto it = plans.find(key);
         if (it != plans.end()) return it->second.get();
         std::unique_ptr<Plan> up(new Plan());
@@ -1085,11 +1087,16 @@ int vb200_destroy(vb200_handle h) {
 const char* vb200_last_error(vb200_handle h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
 
 int vb200_forward(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, void* cuda_stream) {
+    return vb200_forward_slot(h, in, out, select, 0, cuda_stream);
+}
+
+int vb200_forward_slot(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, int32_t slot,
+                       void* cuda_stream) {
     if (h == nullptr) return VB200_ERR_INVALID;
     return guard(h, [&] {
         if (in == nullptr || out == nullptr) fail(VB200_ERR_INVALID, "inputs/outputs struct is NULL");
         CUDA_CHECK(cudaSetDevice(h->opt.device));
-        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL);
+        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL, slot);
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
         h->forward_device(*pl, *in, st);
         h->copy_outputs(*pl, *out, st, cudaMemcpyDeviceToDevice);

@@ -231,12 +231,13 @@ class VILBertForVLTasks(object):
     def forward(self, input_txt, input_imgs, image_loc, token_type_ids=None, attention_mask=None,
                 image_attention_mask=None, co_attention_mask=None, task_ids=None,
                 output_all_encoded_layers=False, output_all_attention_masks=False,
-                compute_pretraining_heads=False, select: Optional[int] = None, debug_taps: bool = False):
+                compute_pretraining_heads=False, select: Optional[int] = None, debug_taps: bool = False, slot: int = 0):
         """Positional signature and 10-tuple of worker.py:286-289.
 
         ``vision_prediction`` / ``linguisic_prediction`` (the pre-training heads, elements 5 and 7, never read
         by the worker) are computed only with ``compute_pretraining_heads=True`` and are ``None`` otherwise;
-        ``attn_data_list`` (element 9, never read by the worker) is returned empty.
+        ``attn_data_list`` (element 9, never read by the worker) is returned empty.  ``slot`` selects one of 16 independent
+        workspaces: calls on different slots may be in flight concurrently on different CUDA streams.
         """
         if self._handle is None:
             if torch.is_tensor(input_txt) and input_txt.is_cuda:
@@ -265,7 +266,7 @@ class VILBertForVLTasks(object):
             setattr(o, k, t.data_ptr())
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            L.check(lib.vb200_forward(self._handle, C.byref(inp), C.byref(o), select, C.c_void_p(stream)), self._handle)
+            L.check(lib.vb200_forward_slot(self._handle, C.byref(inp), C.byref(o), select, slot, C.c_void_p(stream)), self._handle)
         g = outs.get
         result = (g("vil_prediction"), g("vil_prediction_gqa"), g("vil_logit"), g("vil_binary_prediction"),
                   g("vil_tri_prediction"), g("vision_prediction"), g("vision_logit"), g("linguisic_prediction"),
