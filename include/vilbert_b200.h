@@ -143,6 +143,12 @@ int vb200_forward_slot(vb200_handle h, const vb200_inputs* in, const vb200_outpu
 int vb200_forward_host(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select,
                        void* cuda_stream);
 
+/* Same on workspace slot `slot`; synchronize = 0 returns right after enqueueing (H2D copies, kernels and D2H copies are
+ * ordered on `cuda_stream`; the host buffers must stay valid and the outputs are complete once the caller has synchronised
+ * that stream).  Two slots on two streams overlap one batch's copies with the other's kernels. */
+int vb200_forward_host_slot(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, int32_t slot,
+                            int32_t synchronize, void* cuda_stream);
+
 /* Introspection used by the tests / bench: number of kernels one forward of this shape launches,
  * algorithmic FLOPs of it, model dimensions. */
 int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select,

@@ -182,6 +182,42 @@ def test_tiny_model_host_api(tiny_oracle, tiny_engines):
     assert torch.equal(out["vil_prediction"], ref[0].cpu()) and torch.equal(out["vision_logit"], ref[6].cpu())
 
 
+def test_tiny_model_workspace_slots(tiny_oracle, tiny_engines):
+    """vb200_forward_slot / vb200_forward_host_slot: batches in flight on different slots and streams do not disturb each
+    other -- every slot returns bit-for-bit what slot 0 returns for the same batch."""
+    from vilbert_b200 import _lib as L
+    eng = tiny_engines["fp16"]
+    batches = [_tiny_inputs(tiny_oracle, 3, 20, 12, 40 + i, pad=i % 2) for i in range(6)]
+    want = []
+    for b in batches:
+        want.append(eng(*[t.cuda() for t in b])[0].clone())
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    dev = [[t.cuda() for t in b] for b in batches]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        got = []
+        for i, d in enumerate(dev):
+            with torch.cuda.stream(streams[i % 3]):
+                got.append(eng(*d, slot=i % 3)[0].clone())   # clone on the same stream: the slot's buffer is re-used
+        torch.cuda.synchronize()
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
+    # asynchronous host calls, two slots
+    hin = [[t.pin_memory() for i, t in enumerate(b) if i != 6] for b in batches]
+    houts = [{"vil_prediction": torch.empty(3, tiny_oracle.num_labels).pin_memory()} for _ in batches]
+    for i, h in enumerate(hin):
+        s = streams[i % 2]
+        s.synchronize()
+        with torch.cuda.stream(s):
+            eng.forward_host(*h, houts[i], select=L.OUT_VIL_PREDICTION, slot=i % 2, synchronize=False)
+    torch.cuda.synchronize()
+    for w, h in zip(want, houts):
+        assert torch.equal(w.cpu(), h["vil_prediction"])
+    with pytest.raises(RuntimeError):
+        eng(*dev[0], slot=99)
+
+
 @pytest.mark.parametrize("B,Tin,V,pad", [(1, 30, 36, 0), (2, 30, 36, 0), (3, 37, 101, 5), (2, 16, 10, 0)])
 def test_full_model_task_heads(full_oracle, full_engines, parity_log, B, Tin, V, pad):
     from oracle import vilbert_ref as R

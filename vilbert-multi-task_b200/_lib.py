@@ -57,7 +57,7 @@ class Options(C.Structure):
 
 # every symbol include/vilbert_b200.h declares (tests/test_cabi.py checks the list against the header)
 EXPORTS = ["vb200_abi_version", "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_forward", "vb200_forward_slot",
-           "vb200_forward_host", "vb200_plan_info", "vb200_model_dim", "vb200_profile_ops", "vb200_linear", "vb200_layernorm",
+           "vb200_forward_host", "vb200_forward_host_slot", "vb200_plan_info", "vb200_model_dim", "vb200_profile_ops", "vb200_linear", "vb200_layernorm",
            "vb200_self_attention", "vb200_co_attention"]
 
 _lib = None
@@ -89,6 +89,7 @@ def load():
     lib.vb200_forward.argtypes = [vp, C.POINTER(Inputs), C.POINTER(Outputs), u32, vp]
     lib.vb200_forward_slot.argtypes = [vp, C.POINTER(Inputs), C.POINTER(Outputs), u32, i32, vp]
     lib.vb200_forward_host.argtypes = [vp, C.POINTER(Inputs), C.POINTER(Outputs), u32, vp]
+    lib.vb200_forward_host_slot.argtypes = [vp, C.POINTER(Inputs), C.POINTER(Outputs), u32, i32, i32, vp]
     lib.vb200_plan_info.argtypes = [vp, i32, i32, i32, u32, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb200_model_dim.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     lib.vb200_profile_ops.argtypes = [vp, i32, i32, i32, u32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double),

@@ -1104,11 +1104,16 @@ int vb200_forward_slot(vb200_handle h, const vb200_inputs* in, const vb200_outpu
 }
 
 int vb200_forward_host(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, void* cuda_stream) {
+    return vb200_forward_host_slot(h, in, out, select, 0, 1, cuda_stream);
+}
+
+int vb200_forward_host_slot(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, int32_t slot,
+                            int32_t synchronize, void* cuda_stream) {
     if (h == nullptr) return VB200_ERR_INVALID;
     return guard(h, [&] {
         if (in == nullptr || out == nullptr) fail(VB200_ERR_INVALID, "inputs/outputs struct is NULL");
         CUDA_CHECK(cudaSetDevice(h->opt.device));
-        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL);
+        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL, slot);
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
         const size_t B = pl->B, Tin = pl->Tin, V = pl->V, F = h->cfg.v_feat;
         if (pl->d_q == nullptr) {
@@ -1132,7 +1137,7 @@ int vb200_forward_host(vb200_handle h, const vb200_inputs* in, const vb200_outpu
         dev.features = pl->d_feat; dev.spatials = pl->d_loc; dev.image_mask = pl->d_imask; dev.co_attention_mask = nullptr;
         h->forward_device(*pl, dev, st);
         h->copy_outputs(*pl, *out, st, cudaMemcpyDeviceToHost);
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (synchronize) CUDA_CHECK(cudaStreamSynchronize(st));
     });
 }
 

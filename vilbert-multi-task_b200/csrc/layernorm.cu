@@ -13,7 +13,7 @@ namespace vb {
 
 constexpr int kLnMaxVec = 16;   // N <= 2048: float4 per lane per 128 columns
 
-template <bool F16>
+template <bool F16, bool PARTIALS>
 __global__ void __launch_bounds__(256)
 ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long long partial_stride,
                    const float* __restrict__ res, int ld_res,
@@ -32,7 +32,7 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
     for (int k = 0; k < kLnMaxVec; ++k) {
         if (k < nvec) {
             float4 a = yp[lane + 32 * k];
-            for (int sp = 1; sp < n_partials; ++sp) {          // split-K partial sums of the producing GEMM
+            if (PARTIALS) for (int sp = 1; sp < n_partials; ++sp) {          // split-K partial sums of the producing GEMM
                 const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(yp + lane + 32 * k) + sp * partial_stride);
                 a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
             }
@@ -78,11 +78,11 @@ cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long lo
         return cudaErrorInvalidValue;
     const dim3 grid((M + 7) / 8), block(256);
     uint16_t* o16 = reinterpret_cast<uint16_t*>(out16);
-    if (f16)
-        return launch_ex(ln_residual_kernel<true>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, gamma,
-                         beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl);
-    return launch_ex(ln_residual_kernel<false>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, gamma,
-                     beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl);
+#define VB_LN(F, P) launch_ex(ln_residual_kernel<F, P>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, \
+                            gamma, beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl)
+    if (n_partials > 1) return f16 ? VB_LN(true, true) : VB_LN(false, true);
+    return f16 ? VB_LN(true, false) : VB_LN(false, false);
+#undef VB_LN
 }
 
 }  // namespace vb

@@ -277,8 +277,10 @@ class VILBertForVLTasks(object):
 
     # ------------------------------------------------------------------ host-buffer entry (bench e2e, serving)
     def forward_host(self, question, features, spatials, segment_ids, input_mask, image_mask, task_tokens,
-                     out: Dict[str, torch.Tensor], select: int = L.OUT_VIL_PREDICTION):
-        """vb200_forward_host: HOST (ideally pinned) tensors in, HOST tensors out; H2D + forward + D2H + sync."""
+                     out: Dict[str, torch.Tensor], select: int = L.OUT_VIL_PREDICTION, slot: int = 0, synchronize: bool = True):
+        """vb200_forward_host[_slot]: HOST (ideally pinned) tensors in, HOST tensors out; H2D + forward + D2H (+ stream sync).
+        With ``synchronize=False`` the call returns after enqueueing on the current stream; synchronise that stream before
+        reading ``out`` or re-using the input buffers."""
         lib = L.load()
         B, Tin = question.shape
         V = features.shape[1]
@@ -291,6 +293,6 @@ class VILBertForVLTasks(object):
         device = torch.device("cuda", self._device)
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            L.check(lib.vb200_forward_host(self._handle, C.byref(inp), C.byref(o), select, C.c_void_p(stream)),
-                    self._handle)
+            L.check(lib.vb200_forward_host_slot(self._handle, C.byref(inp), C.byref(o), select, slot, 1 if synchronize else 0,
+                                                C.c_void_p(stream)), self._handle)
         return out
