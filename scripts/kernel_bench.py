@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4, help="operand sets cycled through per kernel")
     ap.add_argument("--variant", type=int, default=0, help="0 persistent kernel, 1 one-tile-per-CTA kernel")
     ap.add_argument("--stamps", action="store_true", help="print clock64 phase stamps of the persistent kernel")
+    ap.add_argument("--bn", type=int, default=0, help="override block_n of every plain GEMM")
     a = ap.parse_args()
     lib = L.load()
     B, T, V = a.batch, 31, 36
@@ -72,6 +73,10 @@ def main():
     for name, M, N, K, actf, ln, bn in gemms:
         if a.only and a.only not in name:
             continue
+        if a.variant == 2 and (ln or N % 128 or M < 256):
+            continue
+        if a.bn and not ln:
+            bn = a.bn
         sets = []
         for _ in range(a.sets):
             x = torch.randn(M, K, generator=g, device="cuda").to(act)
@@ -94,11 +99,11 @@ def main():
         fl = 2.0 * M * N * K
         res.append(dict(kernel=name, M=M, N=N, K=K, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
         print(json.dumps(res[-1]), flush=True)
-        if a.stamps and a.variant == 0:
+        if a.stamps and a.variant in (0, 2):
             tb = torch.zeros(16 * 4096, dtype=torch.int64, device="cuda")
             x, w, b, r, ga, be, yb, yf, ldf = sets[0]
             rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
-                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, 0, ptr(tb), C.c_void_p(cur()))
+                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, ptr(tb), C.c_void_p(cur()))
             L.check(rc, None)
             torch.cuda.synchronize()
             t = tb.view(-1, 16).cpu()
@@ -108,6 +113,14 @@ def main():
                      "c0_ld", "c0_res", "c0_math", "c0_store", "c1_ld", "c1_res", "c1_math", "c1_store"]
             print("   stamps (SM cycles since CTA entry, median over %d CTAs): " % len(t) +
                   ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names[:8]) if (t[:, i] != 0).any()), flush=True)
+            lead = t[t[:, 11] != 0]
+            if len(lead):
+                nkb = (K + 63) // 64
+                per = ((lead[:, 10] - lead[:, 2]).double() / (lead[:, 11].double() * nkb))
+                print(f"   steady state: {len(lead)} MMA-issuing CTAs, tiles/CTA median {int(lead[:, 11].median())}, "
+                      f"cycles per k-block median {per.median():.0f} (min {per.min():.0f} max {per.max():.0f}); "
+                      f"producer done {int((t[:, 12] - t[:, 0]).double().median())}, mma done {int((lead[:, 10] - lead[:, 0]).double().median())}, "
+                      f"epilogue done {int((t[:, 13] - t[:, 0]).double().median())}", flush=True)
             g0, g1 = t[:, 8].double(), t[:, 9].double()
             print(f"   globaltimer: kernel span {(g1.max() - g0.min()) / 1e3:.2f} us, CTA start spread {(g0.max() - g0.min()) / 1e3:.2f} us, "
                   f"CTA lifetime median {(g1 - g0).median() / 1e3:.2f} us max {(g1 - g0).max() / 1e3:.2f} us, "

@@ -18,10 +18,10 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-VARIANT = 0     # 0 = persistent kernel (engine default), 1 = one-tile-per-CTA kernel; set per test via the fixture
+VARIANT = 0     # 0 = persistent kernel, 1 = one-tile-per-CTA kernel, 2 = CTA-pair kernel (cta_group::2); set by the fixture
 
 
-@pytest.fixture(params=[0, 1], ids=["persistent", "v1"])
+@pytest.fixture(params=[0, 1, 2], ids=["persistent", "v1", "pair"])
 def variant(request):
     global VARIANT
     VARIANT = request.param
@@ -91,6 +91,8 @@ def _mk(M, N, K, seed=0, act=torch.bfloat16):
 ])
 @pytest.mark.parametrize("act_dt", ACT)
 def test_linear_bias(M, N, K, block_n, act_dt, variant, parity_log):
+    if variant == 2 and (block_n < 128 or N % block_n != 0):
+        pytest.skip("the CTA-pair kernel takes N that is a multiple of its 128/256-wide tile")
     x, w, b, _ = _mk(M, N, K, act=act_dt)
     ld = (N + 3) // 4 * 4
     yb, yf = run_linear(x, w, b, block_n=block_n, ld_f32=ld)
@@ -126,6 +128,8 @@ def test_linear_act(act, act_dt, variant, parity_log):
 ])
 @pytest.mark.parametrize("act_dt", ACT)
 def test_linear_residual_layernorm(M, N, K, act, act_dt, variant, parity_log):
+    if variant == 2:
+        pytest.skip("the CTA-pair kernel has the plain epilogue only")
     x, w, b, g = _mk(M, N, K, seed=2, act=act_dt)
     res = torch.randn(M, N, generator=g, device="cuda")
     gamma = 1.0 + 0.1 * torch.randn(N, generator=g, device="cuda")

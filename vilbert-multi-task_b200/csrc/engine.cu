@@ -302,6 +302,7 @@ struct Op {
     GemmEpilogue ep;
     int block_n = 128;
     bool ln = false;
+    bool pair = false;             // CTA-pair kernel (cta_group::2); tb then has box rows block_n / 2
     // attention
     const bf16 *qkv_a = nullptr, *qkv_b = nullptr;
     int ld_a = 0, ld_b = 0, hidden = 0;
@@ -363,6 +364,11 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
+    // CTA-pair GEMM (cta_group::2, gemm_pair.cu).  -1 = auto: 256-wide pair tiles where a GEMM has >= 4 waves of them (large
+    // batches: +6 % at batch 512); below that the single-CTA kernel wins -- one or two tiles per CTA, where the pair's extra
+    // cluster syncs and coarser tiles cost more than the halved W traffic saves (profiles/README.md).  VB200_PAIR=0|128|256
+    // forces it off / on for every plain GEMM with >= 256 rows.
+    int pair_bn = -1;
     bool fused_ln = false;     // VB200_FUSED_LN=1: cluster-LayerNorm GEMM epilogue instead of GEMM(fp32) + row LayerNorm kernel
     Arena weights;
     std::string last_error;
@@ -627,8 +633,13 @@ struct vb200_engine {
         op.ln = ln != nullptr && !split_ln;
         op.block_n = gemm_v1 ? vb::gemm_pick_block_n(W.N, op.ln) : vb::gemm_p_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
+        if (!gemm_v1 && !op.ln && a_rows >= 256) {
+            if (pair_bn > 0) op.pair = W.N % pair_bn == 0;
+            else if (pair_bn < 0) op.pair = W.N % 256 == 0 && ((a_rows + 255) / 256) * (W.N / 256) >= 4 * (vb::num_sms_host() / 2);
+            if (op.pair) op.block_n = pair_bn > 0 ? pair_bn : 256;
+        }
         op.ta = make_tmap(A, a_rows, W.ldw, lda, 128, opt.act_fp16 != 0);
-        op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.block_n, opt.act_fp16 != 0);
+        op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.pair ? op.block_n / 2 : op.block_n, opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = opt.use_pdl;
@@ -645,7 +656,7 @@ struct vb200_engine {
             // kernel left SMs to the other ViLBERT stream's kernels, the 288-CTA split version does not -- and a split that
             // depends on the tile count would make results depend on the batch size (sharding is bit-exact today).
             // Kept behind VB200_SPLITK=1 for large-K / single-stream use.
-            if (split_k_enabled && !gemm_v1 && act == vb::kActNone && num_kb >= 24 && tiles < 148) {
+            if (split_k_enabled && !gemm_v1 && !op.pair && act == vb::kActNone && num_kb >= 24 && tiles < 148) {
                 split_k = static_cast<int>(std::min<long long>(kMaxSplitK, std::max<long long>(1, 296 / tiles)));
                 while (split_k > 1 && num_kb / split_k < 6) --split_k;
             }
@@ -859,6 +870,7 @@ struct vb200_engine {
         switch (op.kind) {
             case Op::GEMM:
                 if (gemm_v1) CUDA_CHECK(vb::launch_gemm(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
+                else if (op.pair) CUDA_CHECK(vb::launch_gemm_pair(op.ta, op.tb, op.ep, op.block_n, st));
                 else CUDA_CHECK(vb::launch_gemm_persistent(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
                 break;
             case Op::SELF_ATTN:
@@ -1065,6 +1077,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
+        if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
@@ -1206,18 +1219,20 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
                  int32_t block_n, int32_t use_pdl, int32_t act_fp16, int32_t variant, long long* timing, void* cuda_stream) {
     return op_guard([&] {
         const bool ln = gamma != nullptr;
+        const bool pair = variant == 2;                                    // CTA-pair kernel: block_n 128 (default) or 256
         int bn = block_n > 0 ? block_n
-                             : (variant == 1 ? vb::gemm_pick_block_n(static_cast<int>(N), ln)
-                                             : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
+                             : (pair ? 128 : variant == 1 ? vb::gemm_pick_block_n(static_cast<int>(N), ln)
+                                                          : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
         if (bn == 0) fail(VB200_ERR_INVALID, "no tiling for N=%lld with LayerNorm", (long long)N);
         CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128, act_fp16 != 0);
-        CUtensorMap tb = make_tmap(w_bf16, N, K, ld_w, bn, act_fp16 != 0);
+        CUtensorMap tb = make_tmap(w_bf16, N, K, ld_w, pair ? bn / 2 : bn, act_fp16 != 0);
         GemmEpilogue e{};
         e.M = (int)M; e.N = (int)N; e.K = (int)K; e.bias = bias; e.res = residual; e.ld_res = (int)ld_res;
         e.gamma = gamma; e.beta = beta; e.eps = eps; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = (int)ld_y_bf16;
         e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.pdl = use_pdl;
         e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16; e.timing = timing;
         if (variant == 1) CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
+        else if (pair) CUDA_CHECK(vb::launch_gemm_pair(ta, tb, e, bn, static_cast<cudaStream_t>(cuda_stream)));
         else CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
     });
 }

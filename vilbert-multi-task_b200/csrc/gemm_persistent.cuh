@@ -442,6 +442,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 umma_commit(&tmem_full_bar[acc]);
                 if (stamps && it == 0) stamps[3] = clock64();
             }
+            if (stamps) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
         }
         __syncwarp();
     } else {

@@ -1,4 +1,5 @@
 // LayerNorm-fused (cluster) instantiations of the persistent tcgen05 GEMM; see gemm_persistent.cuh.
+#include <cstdlib>
 #include "gemm_persistent.cuh"
 
 namespace vb {
@@ -36,7 +37,11 @@ int gemm_p_max_clusters(int block_n, int cluster) {
 }
 
 int gemm_p_pick_block_n(int N, bool ln) {
-    if (!ln) return N <= 64 ? 64 : 128;
+    if (!ln) {
+        static const int forced = [] { const char* e = getenv("VB200_BN"); return e ? atoi(e) : 0; }();   // A/B switch
+        if ((forced == 64 || forced == 128 || forced == 256) && N % forced == 0) return forced;
+        return N <= 64 ? 64 : 128;
+    }
     static const int cands[5] = {128, 96, 192, 256, 64};
     for (int ci = 0; ci < 5; ++ci) {
         const int bn = cands[ci];

@@ -39,6 +39,10 @@ int gemm_p_pick_block_n(int N, bool ln);
 int gemm_p_max_clusters(int block_n, int cluster);
 cudaError_t launch_gemm_persistent(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep,
                                    int block_n, bool ln, cudaStream_t st);
+int num_sms_host();          // SM count of the current device (148 on B200)
+// CTA-pair kernel (gemm_pair.cu, tcgen05 cta_group::2, 256 x block_n tile per pair); tmap_b box rows = block_n / 2
+cudaError_t launch_gemm_pair(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep, int block_n,
+                             cudaStream_t stream);
 cudaError_t launch_gemm_persistent_plain(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep,
                                          int block_n, cudaStream_t st);
 
