@@ -46,6 +46,7 @@ def parse():
                    help="16-bit format of the tensor-core operands (same tcgen05 rate; fp16 is the engine default, see DESIGN.md 2)")
     p.add_argument("--inflight", type=int, default=2,
                    help="batches in flight per GPU: steps alternate over this many CUDA streams / engine workspace slots")
+    p.add_argument("--ops-table", default="", help="write the per-shape kernel time table (isolated graph replays) to this file")
     p.add_argument("--fused-ln", action="store_true", help="cluster-LayerNorm GEMM epilogue instead of GEMM + row LayerNorm")
     return p.parse_args()
 
@@ -285,6 +286,18 @@ def run_b200(args):
     tflops = flops * args.steps / (ms * 1e-3) / 1e12           # per GPU (ms is the max over ranks)
     # ---- per-kernel times, live: every kernel of the step replayed from its own CUDA graph between two CUDA events
     ops = model.profile_ops(B, Tin, V, select, iters=5)
+    if args.ops_table:
+        agg = {}
+        for o in ops:
+            k = (o["kind"],) + tuple(o["dims"])
+            a_ = agg.setdefault(k, [0, 0.0, 0.0])
+            a_[0] += 1; a_[1] += o["ms"]; a_[2] += o["flops"]
+        rows = [dict(kind=k[0], dims=list(k[1:]), launches=v[0], total_us=round(v[1] * 1e3, 1), us=round(v[1] * 1e3 / v[0], 2),
+                     tflops=round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[2] else None) for k, v in agg.items()]
+        rows.sort(key=lambda r: -r["total_us"])
+        with open(args.ops_table, "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
     fam = {}
     for o in ops:
         f = fam.setdefault(o["kind"], {"launches": 0, "ms": 0.0, "flops": 0.0})

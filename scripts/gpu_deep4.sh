@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/deep.log 2>&1
+VB200_DEEP=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/nodeep.log 2>&1
+timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --inflight 1 > gpurun_out/deep_if1.log 2>&1
+VB200_DEEP=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --inflight 1 > gpurun_out/nodeep_if1.log 2>&1
+python - <<'PY'
+import json
+for n in ("deep", "nodeep", "deep_if1", "nodeep_if1"):
+    try:
+        j = json.loads(open(f"gpurun_out/{n}.log").read().strip().splitlines()[-1])
+        r = j["roofline"]
+        print(n, round(j["value"]), round(j["ms_per_step"],3), "e2e", round(j["e2e"]["value"]), "gemm TF", round(r["achieved"]), r["families_ms"])
+    except Exception as e:
+        print(n, "ERR", e)
+PY

@@ -68,6 +68,8 @@ def main():
         ("co_txt_qkv", Mt, 3072, 768, 0, False, 0), ("co_dense2_ln", Mt, 768, 1024, 0, True, 0),
         ("text_ffn_in_gelu_bn256", Mt, 3072, 768, 1, False, 256), ("pool_t", B, 1024, 768, 2, False, 0),
         ("vqa_fc0_gelu_ln", B, 2048, 1024, 1, True, 0), ("vqa_fc3", B, 3129, 2048, 0, False, 0),
+        ("plain_text_ffn_out", Mt, 768, 3072, 0, False, 0), ("plain_img_out", Mv, 1024, 1024, 0, False, 0),
+        ("plain_text_attn_out", Mt, 768, 768, 0, False, 0),
     ]
     res = []
     for name, M, N, K, actf, ln, bn in gemms:

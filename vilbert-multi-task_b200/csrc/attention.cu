@@ -186,7 +186,7 @@ self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, 
     float* mask_s = reinterpret_cast<float*>(Vs + Lp * kStride);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
-    if (pdl) { pdl_wait(); pdl_launch_dependents(); }
+    if (pdl) pdl_wait();
 
     const uint16_t* base = qkv + static_cast<size_t>(b) * L * ld_qkv + h * D;
     load_tile<D>(Qs, base, L, Lp, ld_qkv);
@@ -195,6 +195,7 @@ self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, 
     for (int j = threadIdx.x; j < L; j += blockDim.x) mask_s[j] = key_mask_add[b * L + j] * kLog2e;
     cp_async_wait_all();
     __syncthreads();
+    if (pdl) pdl_launch_dependents();       // tiles are staged: the next kernel's prologue may overlap the math
     uint16_t* outp = ctx + static_cast<size_t>(b) * L * ld_ctx + h * D;
     for (int t = warp; t * 16 < L; t += nwarps)
         attend_tile<D, F16>(Qs, Ks, Vs, t * 16, L, L, mask_s, scale_l2, outp, ld_ctx, lane);
@@ -222,7 +223,7 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
     float* mask_txt = mask_img + V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
-    if (pdl) { pdl_wait(); pdl_launch_dependents(); }
+    if (pdl) pdl_wait();
 
     const uint16_t* bi = qkv_img + static_cast<size_t>(b) * V * ld_img + h * D;
     const uint16_t* bt = qkv_txt + static_cast<size_t>(b) * T * ld_txt + h * D;
@@ -242,6 +243,7 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
     load_tile<D>(Vs, bt + 2 * hidden, T, Tp, ld_txt);            // V2
     cp_async_wait_all();
     __syncthreads();
+    if (pdl) pdl_launch_dependents();
     uint16_t* out_v = ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D;
     for (int t = warp; t * 16 < V; t += nwarps)
         attend_tile<D, F16>(Qs, Ks, Vs, t * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane);

@@ -141,7 +141,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     if (p.pdl) {
         pdl_wait();
-        pdl_launch_dependents();
     }
 
     if (warp == 0) {
@@ -195,6 +194,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (stamps) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
         }
+        if (p.pdl && lane == 0) pdl_launch_dependents();    // both CTAs (the peer has no MMA loop): see gemm_persistent.cuh
         __syncwarp();
     } else {
         // ============================================================ epilogue warps (both CTAs, own 128 rows)

@@ -27,7 +27,7 @@ constexpr int kUmmaK = 16;
 
 // EPI8: eight epilogue warps (two column groups per TMEM lane quarter).  LayerNorm tiles, GELU tiles (the erf costs ~16
 // instructions per element: with four warps the epilogue of a 128x128 tile took 11 k cycles, 3.5x its MMA time) and 256-wide tiles.
-template <int BLOCK_N, bool LN, bool EPI8 = LN>
+template <int BLOCK_N, bool LN, bool EPI8 = LN, bool DEEP = false>
 struct PCfg {
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
@@ -39,18 +39,34 @@ struct PCfg {
     // with the row slice in registers) and take the whole ring themselves.
     static constexpr int kEpiWarps = (LN || EPI8) ? 8 : 4;
     static constexpr int kEpiThreads = 32 * kEpiWarps;
-    static constexpr int kThreads = 64 + kEpiThreads;            // warp 0 TMA, warp 1 MMA (+TMEM alloc), then epilogue
-    static constexpr int kMinBlocks = (LN || BLOCK_N >= 192) ? 1 : 2;
+    // warp 0 TMA, warp 1 MMA (+TMEM alloc), then the epilogue warps; DEEP: one more MMA-issuing warp at the end
+    static constexpr int kMmaWarps = DEEP ? 2 : 1;
+    static constexpr int kThreads = 64 + kEpiThreads + 32 * (kMmaWarps - 1);
+    // DEEP: one CTA per SM with the whole ring to itself.  A lone CTA with the 3-stage ring is latency-bound at ~540 cycles per
+    // k-block (3 x 32 KB per ~1600-cycle L2 round trip, measured); GEMMs with no more tiles than SMs (N = 768 / 1024 at batch
+    // 64, every M = 64 head) therefore take the deep ring and 8 epilogue warps (their one epilogue per CTA is fully exposed).
+    static constexpr int kMinBlocks = (LN || BLOCK_N >= 192 || DEEP) ? 1 : 2;
     // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
     // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
     //   plain: 32 rows x 20 words of packed 16-bit pairs;  LN: 32 rows x 33 fp32 (serves the fp32 and the 16-bit output)
     //   plain, 8 warps, two CTAs per SM: only 32 x 12 words fit (16-bit outputs, 16 columns at a time; fp32 falls back to
     //   per-lane stores -- that combination only occurs for the 64-row classifier heads)
-    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : ((EPI8 && BLOCK_N < 192) ? 32 * 12 * 4 : 32 * 20 * 4);
+    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : ((EPI8 && kMinBlocks == 2) ? 32 * 12 * 4 : 32 * 20 * 4);
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
     static constexpr int kStages = kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit);
-    static constexpr uint32_t kTmemCols = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    // Accumulator layout in TMEM.  Normal: two buffers of BLOCK_N columns (epilogue of tile i overlaps the MMAs of tile i+1).
+    // DEEP: ONE buffer of kChains x BLOCK_N columns.  Measured: one thread issues at most one tcgen05.mma per ~134 cycles
+    // whatever the instruction's N (536 cycles per k-block for BLOCK_N = 64, 128 and 256 alike, with 3 or 6 ring stages, with
+    // one or four independent accumulators), i.e. half the tensor rate for a lone CTA with N = 128.  Two CTAs per SM hide that
+    // (two issuing threads); a lone CTA gets a second MMA warp instead: warp 1 takes the even k-blocks of a tile, the last
+    // warp the odd ones, each into its OWN accumulator chain so the fp32 summation order stays fixed (the epilogue adds the
+    // two chains) -- results do not depend on how the two warps interleave.
+    static constexpr int kChains = kMmaWarps;
+    static constexpr int kAccBufs = DEEP ? 1 : 2;
+    static constexpr int kAccCols = kChains * kAccBufs * BLOCK_N;
+    static_assert(kAccCols <= 512, "TMEM has 512 columns");
+    static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     // LN: chunks per epilogue thread (two column halves per TMEM lane quarter)
     static constexpr int kCPT = (kNumChunks + 1) / 2;
     // ring | bias[2][BLOCK_N] gamma beta (4*BLOCK_N f32) | part[2 bufs][2 halves][128] float2 | barriers | tmem ptr
@@ -245,8 +261,10 @@ __device__ __forceinline__ void store16_coalesced_h(uint32_t* st, __nv_bfloat16*
 }
 // fp32 output of one 32x32 chunk (row-per-lane in v) through a [32][17] fp32 transpose buffer, 16 columns at a time:
 // every store instruction writes 8 rows x 64 contiguous bytes (two full sectors per row).
+// nvalid = columns of this chunk that exist (N - ncol); a ragged last chunk (the 3129-wide VQA head) is written with scalar
+// stores from the same transposed layout (per-lane stores to 32 different rows cost ~370 cycles per instruction).
 __device__ __forceinline__ void store_f32_coalesced(float* st, float* out, int ld, int m_warp, int M, int ncol,
-                                                    const float (&v)[32], int lane) {
+                                                    const float (&v)[32], int lane, int nvalid = 32) {
     const int c4 = lane & 3;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -257,9 +275,16 @@ __device__ __forceinline__ void store_f32_coalesced(float* st, float* out, int l
         for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + (lane >> 2);
             const float* s4 = st + r * 17 + c4 * 4;
-            if (m_warp + r < M)
-                *reinterpret_cast<float4*>(out + static_cast<size_t>(m_warp + r) * ld + ncol + 16 * h + c4 * 4) =
-                    make_float4(s4[0], s4[1], s4[2], s4[3]);
+            const int c0 = 16 * h + c4 * 4;
+            if (m_warp + r < M) {
+                float* o4 = out + static_cast<size_t>(m_warp + r) * ld + ncol + c0;
+                if (c0 + 4 <= nvalid) {
+                    *reinterpret_cast<float4*>(o4) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (c0 + j < nvalid) o4[j] = s4[j];
+                }
+            }
         }
         __syncwarp();
     }
@@ -300,14 +325,14 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
     __syncwarp();
 }
 
-template <int BLOCK_N, bool LN, int ACT>
-struct KCfg { using type = PCfg<BLOCK_N, LN, (LN || ACT == kActGelu || BLOCK_N >= 256)>; };
+template <int BLOCK_N, bool LN, int ACT, bool DEEP = false>
+struct KCfg { using type = PCfg<BLOCK_N, LN, (LN || ACT == kActGelu || BLOCK_N >= 256 || DEEP), DEEP>; };
 
-template <int BLOCK_N, bool LN, int ACT, bool F16>
-__global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT>::type::kThreads, KCfg<BLOCK_N, LN, ACT>::type::kMinBlocks)
+template <int BLOCK_N, bool LN, int ACT, bool F16, bool DEEP = false>
+__global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT, DEEP>::type::kThreads, KCfg<BLOCK_N, LN, ACT, DEEP>::type::kMinBlocks)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const GemmEpilogue p, const int num_m_tiles, const int num_n_tiles) {
-    using Cfg = typename KCfg<BLOCK_N, LN, ACT>::type;
+    using Cfg = typename KCfg<BLOCK_N, LN, ACT, DEEP>::type;
     constexpr int kStages = Cfg::kStages;
     constexpr int kNC = Cfg::kNumChunks;
     constexpr int kEpiThreads = Cfg::kEpiThreads;
@@ -363,7 +388,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_full_bar[a], Cfg::kMmaWarps);
             mbar_init(&tmem_empty_bar[a], kEpiThreads);
             mbar_init(&ln_bar[a], LN ? cluster_size : 1u);                   // one arrival per CTA of the cluster
         }
@@ -385,8 +410,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (stamps && threadIdx.x == 0) stamps[1] = clock64();
 
     if (p.pdl) {
-        pdl_wait();
-        pdl_launch_dependents();
+        pdl_wait();       // everything above overlapped the previous kernel's tail; its outputs are visible from here on
     }
 
     if (warp == 0) {
@@ -412,37 +436,47 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ============================================================ MMA issuer
+    } else if (warp == 1 || (Cfg::kMmaWarps == 2 && warp == 2 + Cfg::kEpiWarps)) {
+        // ============================================================ MMA issuer(s)
+        // kMmaWarps == 2: issuer `mi` takes the k-blocks of a tile whose index within the tile has parity mi and accumulates
+        // them in chain mi; both walk the whole ring so their (stage, phase) bookkeeping stays aligned with the producer's.
+        const int mi = warp == 1 ? 0 : 1;
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f32acc(kBlockM, BLOCK_N, F16);
             int s = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
-                const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+                const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;
+                const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                const uint32_t tmem_d = tmem_base + acc * (Cfg::kChains * BLOCK_N) + mi * BLOCK_N;
                 const int ks = LN ? 0 : tile % split_k;
                 const int kb_begin = ks * kbs, kb_end = min(num_kb, (ks + 1) * kbs);
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    mbar_wait(&full_bar[s], phase);
-                    tc_fence_after();
-                    if (stamps && it == 0 && kb == kb_begin) stamps[2] = clock64();
-                    uint8_t* sa = ring + s * Cfg::kStageBytes;
-                    const uint64_t da = umma_desc_kmajor_sw128(sa);
-                    const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
+                    if (Cfg::kMmaWarps == 1 || ((kb - kb_begin) & 1) == mi) {
+                        mbar_wait(&full_bar[s], phase);
+                        tc_fence_after();
+                        if (stamps && it == 0 && kb == kb_begin) stamps[2] = clock64();
+                        uint8_t* sa = ring + s * Cfg::kStageBytes;
+                        const uint64_t da = umma_desc_kmajor_sw128(sa);
+                        const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                            umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb >= kb_begin + Cfg::kMmaWarps || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[s]);
+                    }
                     if (++s == kStages) { s = 0; phase ^= 1u; }
                 }
-                umma_commit(&tmem_full_bar[acc]);
-                if (stamps && it == 0) stamps[3] = clock64();
+                umma_commit(&tmem_full_bar[acc]);                      // one arrival per issuing warp
+                if (stamps && it == 0 && mi == 0) stamps[3] = clock64();
             }
-            if (stamps) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
+            if (stamps && mi == 0) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
+            // This CTA's tensor work is issued: let the next kernel's CTAs come up while the epilogue drains (their
+            // griddepcontrol.wait still holds them until this whole grid has finished).  Triggering at kernel entry instead made
+            // the dependents sit on the second CTA slot of every SM for the whole main loop (measured: step 6 % slower).
+            if (p.pdl && mi == 0) pdl_launch_dependents();
         }
         __syncwarp();
     } else {
@@ -455,19 +489,20 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const bool st_fast = (p.out_bf16 == nullptr || (p.ld_bf16 & 7) == 0) && (p.out_f32 == nullptr || (p.ld_f32 & 3) == 0);
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
-            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;
+            const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
             const int mn = LN ? tile : tile / split_k;
             const int ks = LN ? 0 : tile % split_k;
             const int m0 = (LN ? tile : mn / num_n_tiles) * kBlockM;
             const int n0 = (LN ? static_cast<int>(my_rank) : mn % num_n_tiles) * BLOCK_N;
             const int m = m0 + row;
             const bool m_ok = m < p.M;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (Cfg::kChains * BLOCK_N);
             const bool stamp = stamps && it == 0 && et == 0;
 
             if constexpr (!LN) {
                 // ------------------------------------------------ plain epilogue: 4 warps, chunk-pipelined
-                float* bias_t = s_bias + acc * BLOCK_N;
+                float* bias_t = s_bias + (it & 1u) * BLOCK_N;
                 // per-tile bias slice, double-buffered by accumulator parity; the named barrier also orders this tile's
                 // writes after every epilogue warp has finished the tile that last used the buffer
                 for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_t[i] = (p.bias && ks == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
@@ -485,15 +520,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                     uint8_t* xb = s_xpose + ew * Cfg::kXposeBytesPerWarp;
                     constexpr bool kBigBuf = Cfg::kXposeBytesPerWarp >= 32 * 20 * 4;
-                    const bool fast16 = st_fast && nc + 32 <= p.N && p.out_bf16 != nullptr;
-                    const bool fast32 = st_fast && nc + 32 <= p.N && p.out_f32 != nullptr && kBigBuf;   // all warp-uniform
-                    if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
+                    const int nvalid = p.N - nc;                                   // < 32 in a ragged last chunk, <= 0 beyond N
+                    const bool fast16 = st_fast && nvalid >= 32 && p.out_bf16 != nullptr;
+                    const bool fast32 = st_fast && nvalid > 0 && p.out_f32 != nullptr && kBigBuf;      // all warp-uniform
+                    if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
                     if (fast16) {
                         if constexpr (kBigBuf) store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                         else store16_coalesced_h<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                     }
-                    if (m_ok && ((p.out_f32 != nullptr && !fast32) || (p.out_bf16 != nullptr && !fast16))) {
-                        GemmEpilogue ps = p;                       // per-lane (ragged N / odd stride / small buffer) remainder
+                    if (m_ok && nvalid > 0 && ((p.out_f32 != nullptr && !fast32) || (p.out_bf16 != nullptr && !fast16))) {
+                        GemmEpilogue ps = p;                       // per-lane (ragged 16-bit / odd stride / small buffer) remainder
                         ps.out_f32 = out_f32;
                         if (fast32) ps.out_f32 = nullptr;
                         if (fast16) ps.out_bf16 = nullptr;
@@ -527,6 +563,18 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         float v[32];
                         tmem_ld32_issue(taddr + c * 32, v);
                         tmem_ld_wait();
+                        if constexpr (Cfg::kChains > 1) {                     // add the second issuer's accumulator chain
+                            const int kb_cnt = min(num_kb, (ks + 1) * kbs) - ks * kbs;      // a 1-k-block tile never wrote it
+#pragma unroll
+                            for (int ch = 1; ch < Cfg::kChains; ++ch) {
+                                if (ch >= kb_cnt) break;
+                                float t[32];
+                                tmem_ld32_issue(taddr + ch * BLOCK_N + c * 32, t);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += t[j];
+                            }
+                        }
                         if (ci + 1 == kCPG) {
                             tc_fence_before();
                             mbar_arrive(&tmem_empty_bar[acc]);
@@ -686,10 +734,10 @@ void fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, dim3 grid, in
 }
 
 // resident: LN only -- how many clusters of this size can be co-resident (grid.y is capped to it)
-template <int BLOCK_N, bool LN, int ACT, bool F16>
+template <int BLOCK_N, bool LN, int ACT, bool F16, bool DEEP = false>
 cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int resident, cudaStream_t st) {
-    using Cfg = typename KCfg<BLOCK_N, LN, ACT>::type;
-    auto kern = gemm_persistent_kernel<BLOCK_N, LN, ACT, F16>;
+    using Cfg = typename KCfg<BLOCK_N, LN, ACT, DEEP>::type;
+    auto kern = gemm_persistent_kernel<BLOCK_N, LN, ACT, F16, DEEP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const int n_tiles = (ep.N + BLOCK_N - 1) / BLOCK_N;

@@ -1,12 +1,35 @@
 // Plain (bias / GELU / ReLU / pooled-product) instantiations of the persistent tcgen05 GEMM; see gemm_persistent.cuh.
+#include <cstdlib>
 #include "gemm_persistent.cuh"
 
 namespace vb {
 using namespace pgemm;
 
 template <int BN>
+static cudaError_t dispatch_deep(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, cudaStream_t st) {
+    const bool f16 = ep.a_f16 != 0;
+    switch (ep.act) {
+        case kActNone: return f16 ? launch_p<BN, false, kActNone, true, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActNone, false, true>(ta, tb, ep, 0, st);
+        case kActGelu: return f16 ? launch_p<BN, false, kActGelu, true, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActGelu, false, true>(ta, tb, ep, 0, st);
+        case kActRelu: return f16 ? launch_p<BN, false, kActRelu, true, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActRelu, false, true>(ta, tb, ep, 0, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int BN>
 static cudaError_t dispatch_plain(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, cudaStream_t st) {
     const bool f16 = ep.a_f16 != 0;
+    if constexpr (BN < 192) {
+        // No more tiles than SMs: every CTA is alone on its SM -> deep ring, two MMA-issuing warps, 8 epilogue warps (PCfg::DEEP).
+        // Timed alone that variant is 15-25 % faster for every such GEMM (profiles/README.md), but its 200 KB of shared memory
+        // keep the other stream's / the other in-flight batch's kernels off those SMs: with two batches in flight the step
+        // gets 6-12 % slower when the N = 768 / 1024 GEMMs use it.  Default: only the M <= 128 heads at the end of the step
+        // (nothing to overlap with there).  VB200_DEEP=0 never, =1 for every GEMM with <= #SM tiles.
+        static const int deep_mode = [] { const char* e = getenv("VB200_DEEP"); return e ? atoi(e) : 2; }();
+        const long long tiles = static_cast<long long>((ep.M + kBlockM - 1) / kBlockM) * ((ep.N + BN - 1) / BN) * (ep.split_k > 1 ? ep.split_k : 1);
+        if (deep_mode != 0 && tiles <= num_sms() && (deep_mode == 1 || ep.M <= kBlockM))
+            return dispatch_deep<BN>(ta, tb, ep, st);
+    }
     switch (ep.act) {
         case kActNone: return f16 ? launch_p<BN, false, kActNone, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActNone, false>(ta, tb, ep, 0, st);
         case kActGelu: return f16 ? launch_p<BN, false, kActGelu, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActGelu, false>(ta, tb, ep, 0, st);

@@ -19,7 +19,7 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
                    const float* __restrict__ res, int ld_res,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ out_f32, int ld_f32, uint16_t* __restrict__ out16, int ld16, int M, int N, int pdl) {
-    if (pdl) { pdl_wait(); pdl_launch_dependents(); }
+    if (pdl) pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -41,6 +41,7 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
             s += a.x + a.y + a.z + a.w;
         }
     }
+    if (pdl) pdl_launch_dependents();       // inputs are in registers: the next kernel's prologue may overlap the rest
     const float mean = warp_sum(s) / static_cast<float>(N);
     float sq = 0.0f;
 #pragma unroll
