@@ -30,12 +30,20 @@ struct PairCfg {
     static constexpr bool kEpi8 = (ACT == kActGelu) || BN >= 256;
     static constexpr int kEpiWarps = kEpi8 ? 8 : 4;
     static constexpr int kEpiThreads = 32 * kEpiWarps;
-    static constexpr int kThreads = 64 + kEpiThreads;
     static constexpr int kMinBlocks = BN >= 256 ? 1 : 2;
+    // One thread issues at most one tcgen05.mma per ~134 cycles (measured, any N).  N = 256: the instruction itself takes 128
+    // cycles, one issuer is enough.  N = 128 (64-cycle instruction) is issue-bound with one issuer; a second issuing warp with
+    // its own accumulator chain (kMmaWarps = 2, implemented below) needs 2 x 128 columns per accumulator, which at two CTAs
+    // per SM leaves no second buffer -- measured at batch 512: 930 cycles per k-block single-buffered with two issuers vs 675
+    // double-buffered with one.  So: one issuer, two buffers; 128-wide pair tiles stay an experiment (VB200_PAIR=128).
+    static constexpr int kMmaWarps = 1;
+    static constexpr int kChains = kMmaWarps;
+    static constexpr int kAccBufs = 2;                             // TMEM: kChains x kAccBufs x BN columns <= 512 / CTAs per SM
+    static constexpr int kThreads = 64 + kEpiThreads + 32 * (kMmaWarps - 1);
     static constexpr int kXposeBytesPerWarp = (kEpi8 && kMinBlocks == 2) ? 32 * 12 * 4 : 32 * 20 * 4;
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kStages = kMinBlocks == 2 ? 4 : 6;
-    static constexpr uint32_t kTmemCols = 2 * BN;                  // double-buffered accumulator, 128 lanes x BN fp32 each
+    static constexpr uint32_t kTmemCols = kChains * kAccBufs * BN;   // 256 (BN 128, two CTAs per SM) or 512 (BN 256)
     static constexpr int kNumBars = 2 * kStages + 4;
     static constexpr int kSmemAux = 2 * BN * 4 + kNumBars * 8 + 16 + kXposeBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux + 1024;
@@ -126,7 +134,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_init(&empty_bar[s], 1);                // one multicast commit
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full_bar[a], 1);            // one multicast commit
+            mbar_init(&tmem_full_bar[a], Cfg::kMmaWarps);   // one multicast commit per issuing warp
             mbar_init(&tmem_empty_bar[a], 2 * Cfg::kEpiWarps);   // one arrive per epilogue warp of either CTA
         }
         mbar_fence_init();
@@ -164,37 +172,41 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (stamps) stamps[12] = clock64();
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ============================================================ MMA issuer (leader CTA only)
+    } else if (warp == 1 || (Cfg::kMmaWarps == 2 && warp == 2 + Cfg::kEpiWarps)) {
+        // ============================================================ MMA issuer(s) (leader CTA only)
+        const int mi = warp == 1 ? 0 : 1;               // issuer mi: k-blocks of parity mi, accumulator chain mi
         if (leader && lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f32acc(2 * kBlockM, BN, F16);
             int s = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
-                const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+                const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;
+                const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
                 mbar_wait_acquire_cluster(&tmem_empty_bar[acc], acc_phase ^ 1u);   // both CTAs' epilogues drained it
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * (Cfg::kChains * BN) + mi * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[s], phase);                                  // both CTAs' halves have landed
-                    tc_fence_after();
-                    if (stamps && it == 0 && kb == 0) stamps[2] = clock64();
-                    uint8_t* sa = ring + s * Cfg::kStageBytes;
-                    const uint64_t da = umma_desc_kmajor_sw128(sa);
-                    const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
+                    if (Cfg::kMmaWarps == 1 || (kb & 1) == mi) {
+                        mbar_wait(&full_bar[s], phase);                              // both CTAs' halves have landed
+                        tc_fence_after();
+                        if (stamps && it == 0 && kb == 0) stamps[2] = clock64();
+                        uint8_t* sa = ring + s * Cfg::kStageBytes;
+                        const uint64_t da = umma_desc_kmajor_sw128(sa);
+                        const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_pair_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit_pair(&empty_bar[s], 3);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                            umma_pair_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb >= Cfg::kMmaWarps || k > 0) ? 1u : 0u);
+                        umma_commit_pair(&empty_bar[s], 3);
+                    }
                     if (++s == kStages) { s = 0; phase ^= 1u; }
                 }
                 umma_commit_pair(&tmem_full_bar[acc], 3);
-                if (stamps && it == 0) stamps[3] = clock64();
+                if (stamps && it == 0 && mi == 0) stamps[3] = clock64();
             }
-            if (stamps) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
+            if (stamps && mi == 0) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
         }
-        if (p.pdl && lane == 0) pdl_launch_dependents();    // both CTAs (the peer has no MMA loop): see gemm_persistent.cuh
+        if (p.pdl && lane == 0 && mi == 0) pdl_launch_dependents();    // both CTAs (the peer has no MMA loop): see gemm_persistent.cuh
         __syncwarp();
     } else {
         // ============================================================ epilogue warps (both CTAs, own 128 rows)
@@ -206,15 +218,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t leader_empty0 = mapa_u32(&tmem_empty_bar[0], 0);
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
-            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;
+            const uint32_t acc_phase = Cfg::kAccBufs == 2 ? ((it >> 1) & 1u) : (it & 1u);
             const int m0 = ((tile / num_n_tiles) * 2 + static_cast<int>(rank)) * kBlockM;
             const int n0 = (tile % num_n_tiles) * BN;
             const int m = m0 + row;
             const bool m_ok = m < p.M;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (Cfg::kChains * BN);
             const bool stamp = stamps && it == 0 && et == 0;
 
-            float* bias_t = s_bias + acc * BN;
+            float* bias_t = s_bias + (it & 1u) * BN;
             for (int i = et; i < BN; i += kEpiThreads) bias_t[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
             epi_bar_sync<kEpiThreads>();
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -248,17 +261,44 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     store_chunk<F16>(ps, m, nc, false, v);
                 }
             };
-            if constexpr (Cfg::kEpiWarps == 4) {
-                float va[32], vb[32];
-                tmem_ld32_issue(taddr, va);
+            // chunk c of this CTA's accumulator half (sum of the issuers' chains) -> v
+            auto load_chunk = [&](int c, float (&v)[32]) {
+                tmem_ld32_issue(taddr + c * 32, v);
+                tmem_ld_wait();
+                if constexpr (Cfg::kChains == 2) {
+                    if (num_kb >= 2) {                              // a 1-k-block GEMM never wrote chain 1
 #pragma unroll
-                for (int c = 0; c < kNC; ++c) {
-                    float (&v)[32] = (c & 1) ? vb : va;
-                    float (&vn)[32] = (c & 1) ? va : vb;
-                    tmem_ld_wait();
-                    if (c + 1 < kNC) tmem_ld32_issue(taddr + (c + 1) * 32, vn);
-                    else release_acc();
-                    finish_chunk(v, n0 + c * 32);
+                        for (int h = 0; h < 2; ++h) {               // 16 columns at a time keeps the 8-warp variant in registers
+                            float t[16];
+                            tmem_ld16_issue(taddr + BN + c * 32 + 16 * h, t);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[16 * h + j] += t[j];
+                        }
+                    }
+                }
+            };
+            if constexpr (Cfg::kEpiWarps == 4) {
+                if constexpr (Cfg::kChains == 2) {
+#pragma unroll
+                    for (int c = 0; c < kNC; ++c) {
+                        float v[32];
+                        load_chunk(c, v);
+                        if (c + 1 == kNC) release_acc();
+                        finish_chunk(v, n0 + c * 32);
+                    }
+                } else {
+                    float va[32], vb[32];
+                    tmem_ld32_issue(taddr, va);
+#pragma unroll
+                    for (int c = 0; c < kNC; ++c) {
+                        float (&v)[32] = (c & 1) ? vb : va;
+                        float (&vn)[32] = (c & 1) ? va : vb;
+                        tmem_ld_wait();
+                        if (c + 1 < kNC) tmem_ld32_issue(taddr + (c + 1) * 32, vn);
+                        else release_acc();
+                        finish_chunk(v, n0 + c * 32);
+                    }
                 }
             } else {
                 constexpr int kCPG = kNC / 2;
@@ -267,8 +307,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int ci = 0; ci < kCPG; ++ci) {
                     const int c = g * kCPG + ci;
                     float v[32];
-                    tmem_ld32_issue(taddr + c * 32, v);
-                    tmem_ld_wait();
+                    load_chunk(c, v);
                     if (ci + 1 == kCPG) release_acc();
                     finish_chunk(v, n0 + c * 32);
                 }

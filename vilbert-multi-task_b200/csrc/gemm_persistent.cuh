@@ -129,6 +129,17 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    __syncwarp();
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- straight-line per-chunk epilogue pieces (all flags resolved outside the element loops)
@@ -568,11 +579,14 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                             for (int ch = 1; ch < Cfg::kChains; ++ch) {
                                 if (ch >= kb_cnt) break;
-                                float t[32];
-                                tmem_ld32_issue(taddr + ch * BLOCK_N + c * 32, t);
-                                tmem_ld_wait();
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] += t[j];
+                                for (int h = 0; h < 2; ++h) {
+                                    float t[16];
+                                    tmem_ld16_issue(taddr + ch * BLOCK_N + c * 32 + 16 * h, t);
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[16 * h + j] += t[j];
+                                }
                             }
                         }
                         if (ci + 1 == kCPG) {
