@@ -69,15 +69,18 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
     }
 }
 
-// One warp: 16 query rows [r0, r0+16) of Qs against nk keys (Ks/Vs zero-padded to a multiple of 16 rows).
+// One warp: 16 query rows [r0, r0+16) of Qs against nk keys (Ks/Vs zero-padded to a multiple of 16 rows), output columns
+// [oc0, oc0 + OW) of the head.  D = 128 is split into two 64-column work items (S is recomputed by both): 32 instead of 64
+// accumulator registers per thread keep the kernel under 128 registers, i.e. five CTAs per SM and one wave at batch 64
+// (at 170 registers: two CTAs per SM, 1.7 waves -- profiles/r1_attention_ncu.txt).
 // mask_l2[j] = additive key mask * log2(e).  out: 16-bit global, already offset to this head's first column.
-template <int D, bool F16>
+template <int D, int OW, bool F16>
 __device__ __forceinline__ void attend_tile(const uint16_t* Qs, const uint16_t* Ks, const uint16_t* Vs, int r0, int nq,
                                             int nk, const float* mask_l2, float scale_l2, uint16_t* out, int ld_out,
-                                            int lane) {
+                                            int lane, int oc0) {
     constexpr int kStride = AttnTile<D>::kStride;
     constexpr int kKSteps = D / 16;         // k-steps of Q K^T
-    constexpr int kONTiles = D / 8;         // 8-wide output column tiles
+    constexpr int kONTiles = OW / 8;        // 8-wide output column tiles of this work item
     const int g = lane >> 2, tq = lane & 3;  // row within 8, column pair within 8
 
     uint32_t qa[kKSteps][4];
@@ -153,7 +156,7 @@ __device__ __forceinline__ void attend_tile(const uint16_t* Qs, const uint16_t* 
 #pragma unroll
                 for (int nt2 = 0; nt2 < kONTiles / 2; ++nt2) {
                     uint32_t vf[4];   // V[keys kk*16..+16][cols nt2*16..+16] transposed on load
-                    ldsm_x4_trans(vf, Vs + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kStride + nt2 * 16 + (lane >> 4) * 8);
+                    ldsm_x4_trans(vf, Vs + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kStride + oc0 + nt2 * 16 + (lane >> 4) * 8);
                     mma16816<F16>(o[2 * nt2], pa, vf[0], vf[1]);
                     mma16816<F16>(o[2 * nt2 + 1], pa, vf[2], vf[3]);
                 }
@@ -166,14 +169,14 @@ __device__ __forceinline__ void attend_tile(const uint16_t* Qs, const uint16_t* 
     const int row0 = r0 + g, row1 = r0 + g + 8;
 #pragma unroll
     for (int nt = 0; nt < kONTiles; ++nt) {
-        const int col = nt * 8 + tq * 2;
+        const int col = oc0 + nt * 8 + tq * 2;
         if (row0 < nq) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row0) * ld_out + col) = pack16x2<F16>(o[nt][0] * i0, o[nt][1] * i0);
         if (row1 < nq) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row1) * ld_out + col) = pack16x2<F16>(o[nt][2] * i1, o[nt][3] * i1);
     }
 }
 
 template <int D, bool F16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)     // <= 128 registers: 5 CTAs of 3-4 warps per SM -> one wave at batch 64
 self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, const float* __restrict__ key_mask_add,
                       uint16_t* __restrict__ ctx, int ld_ctx, int L, float scale_l2, int pdl) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -197,12 +200,13 @@ self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, 
     __syncthreads();
     if (pdl) pdl_launch_dependents();       // tiles are staged: the next kernel's prologue may overlap the math
     uint16_t* outp = ctx + static_cast<size_t>(b) * L * ld_ctx + h * D;
-    for (int t = warp; t * 16 < L; t += nwarps)
-        attend_tile<D, F16>(Qs, Ks, Vs, t * 16, L, L, mask_s, scale_l2, outp, ld_ctx, lane);
+    constexpr int kSplit = D / 64, kOW = D / kSplit;             // work item = (16-row tile, 64-column slice of the head)
+    for (int w = warp; (w / kSplit) * 16 < L; w += nwarps)
+        attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, L, L, mask_s, scale_l2, outp, ld_ctx, lane, (w % kSplit) * kOW);
 }
 
 template <int D, bool F16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint16_t* __restrict__ qkv_txt, int ld_txt,
                     int hidden, const float* __restrict__ img_mask_add, const float* __restrict__ txt_mask_add,
                     uint16_t* __restrict__ ctx_txt, int ld_ctx_txt, uint16_t* __restrict__ ctx_img, int ld_ctx_img, int T,
@@ -235,8 +239,9 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
     cp_async_wait_all();
     __syncthreads();
     uint16_t* out_t = ctx_txt + static_cast<size_t>(b) * T * ld_ctx_txt + h * D;
-    for (int t = warp; t * 16 < T; t += nwarps)
-        attend_tile<D, F16>(Qs, Ks, Vs, t * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane);
+    constexpr int kSplit = D / 64, kOW = D / kSplit;
+    for (int w = warp; (w / kSplit) * 16 < T; w += nwarps)
+        attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane, (w % kSplit) * kOW);
     __syncthreads();                                             // everyone is done reading phase-1 tiles
     load_tile<D>(Qs, bi, V, Vp, ld_img);                         // Q1
     load_tile<D>(Ks, bt + hidden, T, Tp, ld_txt);                // K2
@@ -245,8 +250,8 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
     __syncthreads();
     if (pdl) pdl_launch_dependents();
     uint16_t* out_v = ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D;
-    for (int t = warp; t * 16 < V; t += nwarps)
-        attend_tile<D, F16>(Qs, Ks, Vs, t * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane);
+    for (int w = warp; (w / kSplit) * 16 < V; w += nwarps)
+        attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane, (w % kSplit) * kOW);
 }
 
 template <int D, bool F16>
@@ -257,7 +262,7 @@ static cudaError_t launch_self(const __nv_bfloat16* qkv, int ld_qkv, int hidden,
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = set_smem(self_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    const int nwarps = min(8, Lp / 16);                       // one warp per 16 query rows (extra staging-only warps measured slower)
+    const int nwarps = min(8, (Lp / 16) * (D / 64));          // one warp per (16 query rows, 64 output columns) work item
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv), ld_qkv, hidden, key_mask_add, reinterpret_cast<uint16_t*>(ctx),
@@ -287,7 +292,7 @@ static cudaError_t launch_co(const __nv_bfloat16* qkv_img, int ld_img, const __n
     if (smem > 227 * 1024) return cudaErrorInvalidValue;     // sequence too long for one CTA's shared memory
     cudaError_t e = set_smem(co_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    const int nwarps = max(4, min(8, Lp / 16));               // >= 4 warps so the cp.async staging is spread over 128 threads
+    const int nwarps = max(4, min(8, (Lp / 16) * (D / 64)));  // >= 4 warps so the cp.async staging is spread over 128 threads
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv_img), ld_img, reinterpret_cast<const uint16_t*>(qkv_txt), ld_txt,
