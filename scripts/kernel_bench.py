@@ -123,6 +123,9 @@ def main():
                       f"cycles per k-block median {per.median():.0f} (min {per.min():.0f} max {per.max():.0f}); "
                       f"producer done {int((t[:, 12] - t[:, 0]).double().median())}, mma done {int((lead[:, 10] - lead[:, 0]).double().median())}, "
                       f"epilogue done {int((t[:, 13] - t[:, 0]).double().median())}", flush=True)
+            if (t[:, 14] != 0).any():
+                print(f"   epilogue of warp 2: acc_ready -> first chunk loaded {int((t[:, 14] - t[:, 4]).double().median())}, "
+                      f"-> first chunk stored {int((t[:, 15] - t[:, 4]).double().median())}, -> done {int((t[:, 7] - t[:, 4]).double().median())}", flush=True)
             g0, g1 = t[:, 8].double(), t[:, 9].double()
             print(f"   globaltimer: kernel span {(g1.max() - g0.min()) / 1e3:.2f} us, CTA start spread {(g0.max() - g0.min()) / 1e3:.2f} us, "
                   f"CTA lifetime median {(g1 - g0).median() / 1e3:.2f} us max {(g1 - g0).max() / 1e3:.2f} us, "

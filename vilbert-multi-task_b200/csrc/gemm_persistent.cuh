@@ -300,6 +300,36 @@ __device__ __forceinline__ void store_f32_coalesced(float* st, float* out, int l
         __syncwarp();
     }
 }
+// Same through the 32 x 12-word buffer of the 8-warp / two-CTAs-per-SM configuration: 8 columns at a time, every store
+// instruction writes 16 rows x 32 contiguous bytes (one full sector per row).
+__device__ __forceinline__ void store_f32_coalesced_q(float* st, float* out, int ld, int m_warp, int M, int ncol,
+                                                      const float (&v)[32], int lane, int nvalid = 32) {
+    constexpr int S = 12;
+    const int piece = lane & 1;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        *reinterpret_cast<float4*>(st + lane * S) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+        *reinterpret_cast<float4*>(st + lane * S + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int r = it * 16 + (lane >> 1);
+            const float4 u = *reinterpret_cast<const float4*>(st + r * S + 4 * piece);
+            const int c0 = 8 * h + 4 * piece;
+            if (m_warp + r < M) {
+                float* o4 = out + static_cast<size_t>(m_warp + r) * ld + ncol + c0;
+                if (c0 + 4 <= nvalid) {
+                    *reinterpret_cast<float4*>(o4) = u;
+                } else {
+                    if (c0 + 0 < nvalid) o4[0] = u.x;
+                    if (c0 + 1 < nvalid) o4[1] = u.y;
+                    if (c0 + 2 < nvalid) o4[2] = u.z;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
 // LayerNorm outputs (fp32 stream copy and 16-bit GEMM operand) of one chunk from an fp32 [32][33] transpose buffer.
 template <bool F16>
 __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue& p, int m_warp, int ncol, const float (&v)[32],
@@ -337,7 +367,9 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
 }
 
 template <int BLOCK_N, bool LN, int ACT, bool DEEP = false>
-struct KCfg { using type = PCfg<BLOCK_N, LN, (LN || ACT == kActGelu || BLOCK_N >= 256 || DEEP), DEEP>; };
+struct KCfg { using type = PCfg<BLOCK_N, LN, true, DEEP>; };   // 8 epilogue warps everywhere: with 4, each SM sub-partition
+                                                                 // runs ONE epilogue warp -- every dependent instruction pays
+                                                                 // its full latency (~4 k cycles per 128x128 tile, measured)
 
 template <int BLOCK_N, bool LN, int ACT, bool F16, bool DEEP = false>
 __global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT, DEEP>::type::kThreads, KCfg<BLOCK_N, LN, ACT, DEEP>::type::kMinBlocks)
@@ -349,8 +381,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     constexpr int kEpiThreads = Cfg::kEpiThreads;
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "epilogue works in 32-column chunks");
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the shared array: an integer round trip would turn every
+    // later access into a GENERIC load/store (LD.E / ST.E instead of LDS / STS in the epilogue -- seen in the SASS)
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring = smem;
     float* s_bias = reinterpret_cast<float*>(ring + kStages * Cfg::kStageBytes);   // [2][BLOCK_N]
     float* s_gamma = s_bias + 2 * BLOCK_N;                                          // LN only (zero-sized otherwise)
@@ -533,8 +567,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     constexpr bool kBigBuf = Cfg::kXposeBytesPerWarp >= 32 * 20 * 4;
                     const int nvalid = p.N - nc;                                   // < 32 in a ragged last chunk, <= 0 beyond N
                     const bool fast16 = st_fast && nvalid >= 32 && p.out_bf16 != nullptr;
-                    const bool fast32 = st_fast && nvalid > 0 && p.out_f32 != nullptr && kBigBuf;      // all warp-uniform
-                    if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
+                    const bool fast32 = st_fast && nvalid > 0 && p.out_f32 != nullptr;                 // all warp-uniform
+                    if (fast32) {
+                        if constexpr (kBigBuf) store_f32_coalesced(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
+                        else store_f32_coalesced_q(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
+                    }
                     if (fast16) {
                         if constexpr (kBigBuf) store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                         else store16_coalesced_h<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
@@ -574,6 +611,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         float v[32];
                         tmem_ld32_issue(taddr + c * 32, v);
                         tmem_ld_wait();
+                        if (stamp && ci == 0) stamps[14] = clock64();         // first chunk in registers
                         if constexpr (Cfg::kChains > 1) {                     // add the second issuer's accumulator chain
                             const int kb_cnt = min(num_kb, (ks + 1) * kbs) - ks * kbs;      // a 1-k-block tile never wrote it
 #pragma unroll
@@ -594,6 +632,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             mbar_arrive(&tmem_empty_bar[acc]);
                         }
                         finish_chunk(v, n0 + c * 32);
+                        if (stamp && ci == 0) stamps[15] = clock64();         // first chunk stored
                     }
                 }
                 if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
