@@ -27,8 +27,7 @@ struct PairCfg {
     static constexpr int kStageBytesB = kHalfN * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
     static constexpr int kNumChunks = BN / 32;
-    static constexpr bool kEpi8 = (ACT == kActGelu) || BN >= 256;
-    static constexpr int kEpiWarps = kEpi8 ? 8 : 4;
+    static constexpr int kEpiWarps = 8;
     static constexpr int kEpiThreads = 32 * kEpiWarps;
     static constexpr int kMinBlocks = BN >= 256 ? 1 : 2;
     // One thread issues at most one tcgen05.mma per ~134 cycles (measured, any N).  N = 256: the instruction itself takes 128
@@ -40,15 +39,15 @@ struct PairCfg {
     static constexpr int kChains = kMmaWarps;
     static constexpr int kAccBufs = 2;                             // TMEM: kChains x kAccBufs x BN columns <= 512 / CTAs per SM
     static constexpr int kThreads = 64 + kEpiThreads + 32 * (kMmaWarps - 1);
-    static constexpr int kXposeBytesPerWarp = (kEpi8 && kMinBlocks == 2) ? 32 * 12 * 4 : 32 * 20 * 4;
+    static constexpr int kXposeBytesPerWarp = 2048;                // 32 rows x 64 B, swizzled (store16_sw / store_f32_sw)
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kStages = kMinBlocks == 2 ? 4 : 6;
     static constexpr uint32_t kTmemCols = kChains * kAccBufs * BN;   // 256 (BN 128, two CTAs per SM) or 512 (BN 256)
     static constexpr int kNumBars = 2 * kStages + 4;
-    static constexpr int kSmemAux = 2 * BN * 4 + kNumBars * 8 + 16 + kXposeBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux + 1024;
+    static constexpr int kSmemAux = BN * 4 + kNumBars * 8 + 16 + kXposeBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux;      // no alignment slack, see gemm_persistent.cuh
     static_assert(BN == 128 || BN == 256, "pair tile widths");
-    static_assert(kMinBlocks == 1 ? kSmemBytes <= 232448 : 2 * (kSmemBytes + 1024) <= 232448, "shared memory budget");
+    static_assert(kMinBlocks == 1 ? kSmemBytes <= 232448 : 2 * (kSmemBytes + 1024) <= 233472, "shared memory budget");
 };
 
 // ---- cta_group::2 flavours of the PTX wrappers in common.cuh
@@ -98,11 +97,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the shared array: an integer round trip would turn every
     // later access into a GENERIC load/store (LD.E / ST.E instead of LDS / STS in the epilogue -- seen in the SASS)
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* ring = smem;
-    float* s_bias = reinterpret_cast<float*>(ring + kStages * Cfg::kStageBytes);     // [2][BN]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 2 * BN);               // used in the leader only
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0u) {
+        if (threadIdx.x == 0) printf("vb: dynamic shared memory base %u not 1024-byte aligned\n", smem_u32(smem_raw));
+        __trap();
+    }
+    uint8_t* ring = smem_raw;
+    float* s_bias = reinterpret_cast<float*>(ring + kStages * Cfg::kStageBytes);     // [BN]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BN);                   // used in the leader only
     uint64_t* empty_bar = full_bar + kStages;                                        // per CTA, multicast commit
     uint64_t* tmem_full_bar = empty_bar + kStages;                                   // [2] per CTA, multicast commit
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;                                    // [2] used in the leader only
@@ -229,7 +231,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (Cfg::kChains * BN);
             const bool stamp = stamps && it == 0 && et == 0;
 
-            float* bias_t = s_bias + (it & 1u) * BN;
+            float* bias_t = s_bias;                        // one slice; the tile-end barrier below protects it
             for (int i = et; i < BN; i += kEpiThreads) bias_t[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
             epi_bar_sync<kEpiThreads>();
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -247,15 +249,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
                 }
-                uint8_t* xb = s_xpose + ew * Cfg::kXposeBytesPerWarp;
-                constexpr bool kBigBuf = Cfg::kXposeBytesPerWarp >= 32 * 20 * 4;
+                uint4* xb = reinterpret_cast<uint4*>(s_xpose + ew * Cfg::kXposeBytesPerWarp);
                 const bool fast16 = st_fast && nc + 32 <= p.N && p.out_bf16 != nullptr;
-                const bool fast32 = st_fast && nc + 32 <= p.N && p.out_f32 != nullptr && kBigBuf;
-                if (fast32) store_f32_coalesced(reinterpret_cast<float*>(xb), p.out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
-                if (fast16) {
-                    if constexpr (kBigBuf) store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
-                    else store16_coalesced_h<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
-                }
+                const bool fast32 = st_fast && nc + 32 <= p.N && p.out_f32 != nullptr;
+                if (fast32) store_f32_sw(xb, p.out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane);
+                if (fast16) store16_sw<F16>(xb, p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                 if (m_ok && ((p.out_f32 != nullptr && !fast32) || (p.out_bf16 != nullptr && !fast16))) {
                     GemmEpilogue ps = p;
                     if (fast32) ps.out_f32 = nullptr;
@@ -315,6 +313,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
             if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
+            if (tile + tile_stride < total_tiles) epi_bar_sync<kEpiThreads>();         // bias slice free for the next tile
         }
         if (stamps && et == 0) stamps[13] = clock64();
     }

@@ -51,7 +51,7 @@ struct PCfg {
     //   plain: 32 rows x 20 words of packed 16-bit pairs;  LN: 32 rows x 33 fp32 (serves the fp32 and the 16-bit output)
     //   plain, 8 warps, two CTAs per SM: only 32 x 12 words fit (16-bit outputs, 16 columns at a time; fp32 falls back to
     //   per-lane stores -- that combination only occurs for the 64-row classifier heads)
-    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : ((EPI8 && kMinBlocks == 2) ? 32 * 12 * 4 : 32 * 20 * 4);
+    static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 2048;      // plain: 32 rows x 64 B, swizzled (store16_sw)
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
     static constexpr int kStages = kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit);
@@ -73,9 +73,13 @@ struct PCfg {
     static constexpr int kNumBars = 2 * kStages + 4 + 2;
     // LN-only pieces (gamma, beta, cluster partials) cost nothing in the plain kernel, whose budget is (227 KB - 2 KB) / 2
     static constexpr int kLnAux = LN ? 2 * BLOCK_N * 4 + 4 * kBlockM * 8 : 0;
-    static constexpr int kSmemAux = 2 * BLOCK_N * 4 + kLnAux + kNumBars * 8 + 16 + kXposeBytes;
-    static_assert(kMinBlocks == 1 || 2 * (kStages * kStageBytes + kSmemAux + 1024 + 1024) <= 232448, "two CTAs per SM must fit");
-    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux + 1024;
+    // plain: ONE bias slice (the tile-end barrier of the epilogue warps protects it); LN keeps bias | gamma | beta resident
+    static constexpr int kBiasFloats = LN ? 2 * BLOCK_N : BLOCK_N;
+    static constexpr int kSmemAux = kBiasFloats * 4 + kLnAux + kNumBars * 8 + 16 + kXposeBytes;
+    // no alignment slack: the dynamic shared-memory window starts 1024-aligned (checked at kernel entry).  An SM has 233472
+    // bytes and every CTA costs its dynamic size + 1024 reserved.
+    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux;
+    static_assert(kMinBlocks == 1 ? kSmemBytes <= 232448 : 2 * (kSmemBytes + 1024) <= 233472, "shared memory budget");
 };
 
 // ---- cluster-scope mbarrier helpers (LayerNorm exchange)
@@ -216,13 +220,15 @@ __device__ __forceinline__ void res_add(float (&v)[32], const float4 (&r)[8]) {
     for (int j = 0; j < 8; ++j) { v[4 * j] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w; }
 }
 
-// ---- row-contiguous stores through a per-warp shared-memory transpose
-// 16-bit output of one 32-row x 32-column chunk held row-per-lane in v: pack, transpose, then every store instruction
-// writes 8 rows x 64 contiguous bytes (2 full sectors per row) instead of 32 rows x 16 bytes.
+// ---- row-contiguous stores through a per-warp 2 KB shared-memory transpose (32 rows x 64 bytes, XOR-swizzled)
+// Row r keeps its four 16-byte units j at position j ^ ((r >> 1) & 3): the row-per-lane writes (one unit per instruction) and
+// the 8-rows-per-instruction reads (lane -> row it*8 + lane/4, unit lane%4) are both bank-conflict free, and every global
+// store instruction writes 8 rows x 64 contiguous bytes.  The epilogue is bound by LSU wavefronts (one per 128-byte line
+// touched per instruction): 32-byte row pieces cost twice as many as these 64-byte ones.
+__device__ __forceinline__ int sw_unit(int r, int j) { return r * 4 + (j ^ ((r >> 1) & 3)); }     // in 16-byte units
 template <bool F16>
-__device__ __forceinline__ void store16_coalesced(uint32_t* st, __nv_bfloat16* out, int ld, int m_warp, int M, int ncol,
-                                                  const float (&v)[32], int lane) {
-    constexpr int S = 20;                                  // words per staged row (16 used): 16-byte accesses stay conflict-free
+__device__ __forceinline__ void store16_sw(uint4* st, __nv_bfloat16* out, int ld, int m_warp, int M, int ncol,
+                                           const float (&v)[32], int lane) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint4 u;
@@ -230,106 +236,52 @@ __device__ __forceinline__ void store16_coalesced(uint32_t* st, __nv_bfloat16* o
         u.y = F16 ? pack16x2_rt(v[8 * j + 2], v[8 * j + 3], 1) : pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
         u.z = F16 ? pack16x2_rt(v[8 * j + 4], v[8 * j + 5], 1) : pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
         u.w = F16 ? pack16x2_rt(v[8 * j + 6], v[8 * j + 7], 1) : pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(st + lane * S + 4 * j) = u;
+        st[sw_unit(lane, j)] = u;
     }
     __syncwarp();
-    const int piece = lane & 3;
+    const int j = lane & 3;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2);
-        const uint4 u = *reinterpret_cast<const uint4*>(st + r * S + 4 * piece);
-        if (m_warp + r < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(m_warp + r) * ld + ncol + piece * 8) = u;
+        const uint4 u = st[sw_unit(r, j)];
+        if (m_warp + r < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(m_warp + r) * ld + ncol + j * 8) = u;
     }
     __syncwarp();                                          // staging buffer is reused by the next chunk
 }
-// Same, 16 columns at a time through a 32 x 12-word buffer (the 8-warp plain epilogue has only that much shared memory):
-// every store instruction writes 16 rows x 32 contiguous bytes (one full sector per row).
-template <bool F16>
-__device__ __forceinline__ void store16_coalesced_h(uint32_t* st, __nv_bfloat16* out, int ld, int m_warp, int M, int ncol,
-                                                    const float (&v)[32], int lane) {
-    constexpr int S = 12;
-    const int piece = lane & 1;
+// fp32, 16 columns per pass; nvalid = columns of this chunk that exist (N - ncol): a ragged last chunk (the 3129-wide VQA
+// head) is finished with scalar stores from the same transposed layout.
+__device__ __forceinline__ void store_f32_sw(uint4* st, float* out, int ld, int m_warp, int M, int ncol, const float (&v)[32],
+                                             int lane, int nvalid = 32) {
+    const int j = lane & 3;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            uint4 u;
-            u.x = F16 ? pack16x2_rt(v[16 * h + 8 * j + 0], v[16 * h + 8 * j + 1], 1) : pack_bf16x2(v[16 * h + 8 * j + 0], v[16 * h + 8 * j + 1]);
-            u.y = F16 ? pack16x2_rt(v[16 * h + 8 * j + 2], v[16 * h + 8 * j + 3], 1) : pack_bf16x2(v[16 * h + 8 * j + 2], v[16 * h + 8 * j + 3]);
-            u.z = F16 ? pack16x2_rt(v[16 * h + 8 * j + 4], v[16 * h + 8 * j + 5], 1) : pack_bf16x2(v[16 * h + 8 * j + 4], v[16 * h + 8 * j + 5]);
-            u.w = F16 ? pack16x2_rt(v[16 * h + 8 * j + 6], v[16 * h + 8 * j + 7], 1) : pack_bf16x2(v[16 * h + 8 * j + 6], v[16 * h + 8 * j + 7]);
-            *reinterpret_cast<uint4*>(st + lane * S + 4 * j) = u;
+        for (int jj = 0; jj < 4; ++jj) {
+            const float4 f = make_float4(v[16 * h + 4 * jj], v[16 * h + 4 * jj + 1], v[16 * h + 4 * jj + 2], v[16 * h + 4 * jj + 3]);
+            st[sw_unit(lane, jj)] = *reinterpret_cast<const uint4*>(&f);
         }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int r = it * 16 + (lane >> 1);
-            const uint4 u = *reinterpret_cast<const uint4*>(st + r * S + 4 * piece);
-            if (m_warp + r < M) *reinterpret_cast<uint4*>(out + static_cast<size_t>(m_warp + r) * ld + ncol + 16 * h + piece * 8) = u;
-        }
-        __syncwarp();
-    }
-}
-// fp32 output of one 32x32 chunk (row-per-lane in v) through a [32][17] fp32 transpose buffer, 16 columns at a time:
-// every store instruction writes 8 rows x 64 contiguous bytes (two full sectors per row).
-// nvalid = columns of this chunk that exist (N - ncol); a ragged last chunk (the 3129-wide VQA head) is written with scalar
-// stores from the same transposed layout (per-lane stores to 32 different rows cost ~370 cycles per instruction).
-__device__ __forceinline__ void store_f32_coalesced(float* st, float* out, int ld, int m_warp, int M, int ncol,
-                                                    const float (&v)[32], int lane, int nvalid = 32) {
-    const int c4 = lane & 3;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st[lane * 17 + j] = v[16 * h + j];
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + (lane >> 2);
-            const float* s4 = st + r * 17 + c4 * 4;
-            const int c0 = 16 * h + c4 * 4;
+            const uint4 u = st[sw_unit(r, j)];
+            const float4 f = *reinterpret_cast<const float4*>(&u);
+            const int c0 = 16 * h + 4 * j;
             if (m_warp + r < M) {
                 float* o4 = out + static_cast<size_t>(m_warp + r) * ld + ncol + c0;
                 if (c0 + 4 <= nvalid) {
-                    *reinterpret_cast<float4*>(o4) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                    *reinterpret_cast<float4*>(o4) = f;
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (c0 + j < nvalid) o4[j] = s4[j];
+                    if (c0 + 0 < nvalid) o4[0] = f.x;
+                    if (c0 + 1 < nvalid) o4[1] = f.y;
+                    if (c0 + 2 < nvalid) o4[2] = f.z;
                 }
             }
         }
         __syncwarp();
     }
 }
-// Same through the 32 x 12-word buffer of the 8-warp / two-CTAs-per-SM configuration: 8 columns at a time, every store
-// instruction writes 16 rows x 32 contiguous bytes (one full sector per row).
-__device__ __forceinline__ void store_f32_coalesced_q(float* st, float* out, int ld, int m_warp, int M, int ncol,
-                                                      const float (&v)[32], int lane, int nvalid = 32) {
-    constexpr int S = 12;
-    const int piece = lane & 1;
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-        *reinterpret_cast<float4*>(st + lane * S) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
-        *reinterpret_cast<float4*>(st + lane * S + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int r = it * 16 + (lane >> 1);
-            const float4 u = *reinterpret_cast<const float4*>(st + r * S + 4 * piece);
-            const int c0 = 8 * h + 4 * piece;
-            if (m_warp + r < M) {
-                float* o4 = out + static_cast<size_t>(m_warp + r) * ld + ncol + c0;
-                if (c0 + 4 <= nvalid) {
-                    *reinterpret_cast<float4*>(o4) = u;
-                } else {
-                    if (c0 + 0 < nvalid) o4[0] = u.x;
-                    if (c0 + 1 < nvalid) o4[1] = u.y;
-                    if (c0 + 2 < nvalid) o4[2] = u.z;
-                }
-            }
-        }
-        __syncwarp();
-    }
-}
+
 // LayerNorm outputs (fp32 stream copy and 16-bit GEMM operand) of one chunk from an fp32 [32][33] transpose buffer.
 template <bool F16>
 __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue& p, int m_warp, int ncol, const float (&v)[32],
@@ -383,11 +335,14 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the shared array: an integer round trip would turn every
     // later access into a GENERIC load/store (LD.E / ST.E instead of LDS / STS in the epilogue -- seen in the SASS)
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* ring = smem;
-    float* s_bias = reinterpret_cast<float*>(ring + kStages * Cfg::kStageBytes);   // [2][BLOCK_N]
-    float* s_gamma = s_bias + 2 * BLOCK_N;                                          // LN only (zero-sized otherwise)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0u) {            // SWIZZLE_128B atoms need it; the budget has no slack to re-align
+        if (threadIdx.x == 0) printf("vb: dynamic shared memory base %u not 1024-byte aligned\n", smem_u32(smem_raw));
+        __trap();
+    }
+    uint8_t* ring = smem_raw;
+    float* s_bias = reinterpret_cast<float*>(ring + kStages * Cfg::kStageBytes);   // [BLOCK_N] (LN: [2][BLOCK_N], 2nd half unused)
+    float* s_gamma = s_bias + Cfg::kBiasFloats;                                     // LN only (zero-sized otherwise)
     float* s_beta = s_gamma + (LN ? BLOCK_N : 0);
     float2* s_part = reinterpret_cast<float2*>(s_beta + (LN ? BLOCK_N : 0));        // [2 bufs][2 halves][128] (mean, M2)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + (LN ? 4 * kBlockM : 0));
@@ -547,9 +502,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
             if constexpr (!LN) {
                 // ------------------------------------------------ plain epilogue: 4 warps, chunk-pipelined
-                float* bias_t = s_bias + (it & 1u) * BLOCK_N;
-                // per-tile bias slice, double-buffered by accumulator parity; the named barrier also orders this tile's
-                // writes after every epilogue warp has finished the tile that last used the buffer
+                float* bias_t = s_bias;
+                // per-tile bias slice; the barrier below orders it before the reads, the one at the end of the tile orders
+                // the reads before the next tile's writes
                 for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_t[i] = (p.bias && ks == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
                 epi_bar_sync<kEpiThreads>();
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -563,21 +518,14 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
                     }
-                    uint8_t* xb = s_xpose + ew * Cfg::kXposeBytesPerWarp;
-                    constexpr bool kBigBuf = Cfg::kXposeBytesPerWarp >= 32 * 20 * 4;
+                    uint4* xb = reinterpret_cast<uint4*>(s_xpose + ew * Cfg::kXposeBytesPerWarp);
                     const int nvalid = p.N - nc;                                   // < 32 in a ragged last chunk, <= 0 beyond N
                     const bool fast16 = st_fast && nvalid >= 32 && p.out_bf16 != nullptr;
                     const bool fast32 = st_fast && nvalid > 0 && p.out_f32 != nullptr;                 // all warp-uniform
-                    if (fast32) {
-                        if constexpr (kBigBuf) store_f32_coalesced(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
-                        else store_f32_coalesced_q(reinterpret_cast<float*>(xb), out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
-                    }
-                    if (fast16) {
-                        if constexpr (kBigBuf) store16_coalesced<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
-                        else store16_coalesced_h<F16>(reinterpret_cast<uint32_t*>(xb), p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
-                    }
+                    if (fast32) store_f32_sw(xb, out_f32, p.ld_f32, m0 + q * 32, p.M, nc, v, lane, nvalid);
+                    if (fast16) store16_sw<F16>(xb, p.out_bf16, p.ld_bf16, m0 + q * 32, p.M, nc, v, lane);
                     if (m_ok && nvalid > 0 && ((p.out_f32 != nullptr && !fast32) || (p.out_bf16 != nullptr && !fast16))) {
-                        GemmEpilogue ps = p;                       // per-lane (ragged 16-bit / odd stride / small buffer) remainder
+                        GemmEpilogue ps = p;                       // per-lane (ragged 16-bit / odd stride) remainder
                         ps.out_f32 = out_f32;
                         if (fast32) ps.out_f32 = nullptr;
                         if (fast16) ps.out_bf16 = nullptr;
@@ -636,6 +584,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                 }
                 if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
+                if (tile + tile_stride < total_tiles) epi_bar_sync<kEpiThreads>();     // bias slice free for the next tile
             } else {
                 // ------------------------------------------------ LayerNorm epilogue: 8 warps, row slice in registers
                 constexpr int kCPT = Cfg::kCPT;
