@@ -31,7 +31,7 @@ UNIT = "pairs/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.02)
+                time.sleep(0.003)
         except Exception as e:          # NVML missing: report it, never fail the bench
             self.err = repr(e)
 
