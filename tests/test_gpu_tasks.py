@@ -102,3 +102,73 @@ def test_prediction_on_engine_matches_oracle_decode(full_oracle, engine, task_id
     else:
         assert ans["top3_answer"] == ref["top3_answer"]
         assert ans["top3_confidence"] == pytest.approx(ref["top3_confidence"], abs=5e-3)
+
+
+def test_multitask_b512_full_size_properties(full_oracle, engine, parity_log):
+    """BASELINE.json configs[2] at its full size (B = 512, 64 per GPU on 8 GPUs, task tokens VQA / NLVR2 / RefCOCO in thirds,
+    NLVR2 samples as adjacent pairs).  Size-independent properties: the eight pair-aligned rank slices reproduce the whole-batch
+    outputs bit for bit, and sampled rows match the oracle (which only sees those rows -- pairs are independent)."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import parallel as P
+    B, world = 512, 8
+    inp = list(R.make_inputs(B, 30, 36, seed=4242, pad_regions=1))
+    n3 = (B // 3) // 2 * 2                                    # thirds on pair boundaries: 170 / 170 / 172
+    task = torch.cat([torch.full((n3, 1), 1), torch.full((n3, 1), 12), torch.full((B - 2 * n3, 1), 11)]).long()
+    inp[7] = task
+    dev = [t.cuda() for t in inp]
+    whole = engine(*dev)
+    torch.cuda.synchronize()
+    whole = [w.clone() if torch.is_tensor(w) else w for w in whole]
+    for rank in range(world):
+        lo, hi = P.shard_range(B, rank, world, pair_aligned=True)
+        assert (lo, hi) == (64 * rank, 64 * rank + 64)
+        out = engine(*[t[lo:hi] for t in dev])
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], whole[0][lo:hi])
+        assert torch.equal(out[3], whole[3][lo // 2:hi // 2])
+        assert torch.equal(out[6], whole[6][lo:hi])
+    rows = [0, 1, n3, n3 + 1, 2 * n3, 2 * n3 + 1, B - 2, B - 1]          # pairs (2i, 2i+1) stay together
+    ref = full_oracle(*[t[rows] for t in inp], compute_pretraining_heads=False)
+    errs = {}
+    for i, name in ((0, "vil_prediction"), (6, "vision_logit")):
+        r, o = ref[i], whole[i][rows].cpu()
+        small = r.abs() < 1000
+        errs[name] = float((o - r).abs()[small].max())
+    pair_rows = [r // 2 for r in rows[::2]]
+    errs["vil_binary_prediction"] = float((whole[3][pair_rows].cpu() - ref[3]).abs().max())
+    for name, err in errs.items():
+        parity_log(test="multitask_B512", output=name, max_abs_err=err)
+        assert err < 1e-2, (name, err)
+
+
+def test_retrieval_1000x1000_rank_block(full_oracle, engine, parity_log):
+    """BASELINE.json configs[3] at its full size as ONE rank of eight sees it: 125 of 1000 captions against all 1000 images
+    (125 k pair forwards).  Properties: the block does not depend on how the images are chunked into forwards (bit-exact),
+    and sampled entries match the oracle's vil_logit of that (caption, image) pair."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import parallel as P
+    n_cap, n_img, world, rank = 1000, 1000, 8, 3
+    lo, hi = P.shard_range(n_cap, rank, world)
+    assert hi - lo == 125
+    g = torch.Generator().manual_seed(7007)
+    cap = R.make_inputs(hi - lo, 30, 36, seed=7100 + rank)            # this rank's captions
+    base = R.make_inputs(50, 30, 36, seed=7200)                       # 1000 images = 50 distinct feature sets x 20 variants
+    f = base[1].repeat(20, 1, 1) * (0.75 + 0.5 * torch.rand(n_img, 1, 1, generator=g))
+    s, vm = base[2].repeat(20, 1, 1), base[5].repeat(20, 1)
+    q, seg, im = cap[0], cap[3], cap[4]
+    score = P.make_pair_scorer(engine, (q.cuda(), seg.cuda(), im.cuda()), (f.cuda(), s.cuda(), vm.cuda()))
+    block = torch.stack([torch.cat([score(c, torch.arange(a, min(n_img, a + 250))).reshape(-1).float()
+                                    for a in range(0, n_img, 250)]) for c in range(hi - lo)])
+    torch.cuda.synchronize()
+    assert block.shape == (125, n_img) and torch.isfinite(block).all()
+    for c in (0, 57, 124):                                            # other chunkings of the image axis: same bits
+        again = torch.cat([score(c, torch.arange(a, min(n_img, a + 64))).reshape(-1).float() for a in range(0, n_img, 64)])
+        assert torch.equal(again, block[c])
+    picks = [(0, 0), (3, 999), (57, 500), (124, 123), (99, 731), (64, 64)]
+    worst = 0.0
+    for c, i in picks:
+        out = full_oracle(q[c:c + 1], f[i:i + 1], s[i:i + 1], seg[c:c + 1], im[c:c + 1], vm[i:i + 1], None, torch.full((1, 1), 7),
+                          compute_pretraining_heads=False)
+        worst = max(worst, abs(float(out[2].view(-1)[0]) - float(block[c, i])))
+    parity_log(test="retrieval_1000x1000_rank_block", max_abs_err=worst, ref_std=float(block.std()))
+    assert worst < 1e-2

@@ -215,6 +215,9 @@ __device__ __forceinline__ float dsmem_ld_f32(const float* local_smem_ptr, uint3
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// L2 prefetch of one 128-byte line (no data returned, no register)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ------------------------------------------------------------------ math
 // erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26): branch-free, 2 MUFU + ~10 FMA-class instructions per value.
 // The libdevice erff costs several times more (two range-dependent paths, both executed by a divergent warp), and the

@@ -303,6 +303,8 @@ struct Op {
     int block_n = 128;
     bool ln = false;
     bool pair = false;             // CTA-pair kernel (cta_group::2); tb then has box rows block_n / 2
+    const void* w = nullptr;       // this GEMM's weight matrix (the previous GEMM of the stream prefetches it into L2)
+    long long w_bytes = 0;
     // attention
     const bf16 *qkv_a = nullptr, *qkv_b = nullptr;
     int ld_a = 0, ld_b = 0, hidden = 0;
@@ -364,6 +366,7 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
+    bool weight_prefetch = true;    // VB200_PREFETCH=0 disables the L2 prefetch of the next GEMM's weights
     // CTA-pair GEMM (cta_group::2, gemm_pair.cu).  -1 = auto: 256-wide pair tiles where a GEMM has >= 4 waves of them (large
     // batches: +6 % at batch 512); below that the single-CTA kernel wins -- one or two tiles per CTA, where the pair's extra
     // cluster syncs and coarser tiles cost more than the halved W traffic saves (profiles/README.md).  VB200_PAIR=0|128|256
@@ -668,6 +671,8 @@ struct vb200_engine {
             e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f;
         }
         op.flops = 2.0 * a_rows * W.N * W.K;
+        op.w = W.w;
+        op.w_bytes = static_cast<long long>(W.N) * W.ldw * 2;
         pl.flops += op.flops;
         pl.ops.push_back(op);
         if (split_ln) {
@@ -849,6 +854,7 @@ struct vb200_engine {
         }
         for (Op& op : ops) if (op.kind == Op::ROWDOT) pl.flops += op.flops;
 
+        link_prefetch(pl);
         // One eager pass first: opts kernels into their shared-memory sizes and surfaces launch-configuration
         // errors with a real message (errors inside a capture only invalidate the capture).
         {
@@ -961,6 +967,26 @@ struct vb200_engine {
         }
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     }
+    // Every GEMM pulls the weights of the next GEMM of its graph branch into L2 while its own main loop runs (GemmEpilogue::
+    // prefetch).  The last GEMM of a branch prefetches the first weights of the step (the next batch starts there).
+    void link_prefetch(Plan& pl) {
+        if (!weight_prefetch) return;
+        const int n = static_cast<int>(pl.ops.size());
+        for (int i = 0; i < n; ++i) {
+            Op& a = pl.ops[i];
+            if (a.kind != Op::GEMM) continue;
+            int next = -1, any = -1;
+            for (int j = i + 1; j < n && next < 0; ++j) {
+                if (pl.ops[j].kind != Op::GEMM) continue;
+                if (any < 0) any = j;
+                if (pl.ops[j].stream == a.stream) next = j;
+            }
+            if (next < 0) next = any;
+            if (next < 0) for (int j = 0; j < i && next < 0; ++j) if (pl.ops[j].kind == Op::GEMM) next = j;
+            if (next >= 0) { a.ep.prefetch = pl.ops[next].w; a.ep.prefetch_bytes = pl.ops[next].w_bytes; }
+        }
+    }
+
     void capture(Plan& pl) {
         cudaStream_t cs;
         CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -1077,6 +1103,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
+        if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));

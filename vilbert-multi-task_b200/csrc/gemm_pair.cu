@@ -220,6 +220,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int et = threadIdx.x - 64;
         const bool st_fast = (p.out_bf16 == nullptr || (p.ld_bf16 & 7) == 0) && (p.out_f32 == nullptr || (p.ld_f32 & 3) == 0);
         const uint32_t leader_empty0 = mapa_u32(&tmem_empty_bar[0], 0);
+        if (p.prefetch != nullptr) {                     // next GEMM's weights -> L2 (see gemm_persistent.cuh)
+            const long long lines = (p.prefetch_bytes + 127) >> 7;
+            const long long nthr = static_cast<long long>(gridDim.x) * kEpiThreads;
+            for (long long l = static_cast<long long>(blockIdx.x) * kEpiThreads + et; l < lines; l += nthr)
+                prefetch_l2(static_cast<const uint8_t*>(p.prefetch) + (l << 7));
+        }
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
             const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;

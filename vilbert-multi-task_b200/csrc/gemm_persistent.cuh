@@ -487,6 +487,13 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;
         const bool st_fast = (p.out_bf16 == nullptr || (p.ld_bf16 & 7) == 0) && (p.out_f32 == nullptr || (p.ld_f32 & 3) == 0);
+        if (p.prefetch != nullptr) {
+            // nothing to do until the first accumulator is ready: pull the next GEMM's weights into L2, one line per thread
+            const long long lines = (p.prefetch_bytes + 127) >> 7;
+            const long long nthr = static_cast<long long>(gridDim.x) * gridDim.y * kEpiThreads;
+            for (long long l = (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * kEpiThreads + et; l < lines; l += nthr)
+                prefetch_l2(static_cast<const uint8_t*>(p.prefetch) + (l << 7));
+        }
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
             const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;

@@ -28,7 +28,9 @@ struct GemmEpilogue {
     int split_k;                  // plain kernel only: K is cut into split_k slices, slice s writes its fp32 partial sum to
     long long split_stride;       //   out_f32 + s * split_stride (bias added by slice 0); the row LayerNorm kernel sums them
     long long* timing;            // optional (profiling): 8 clock64 stamps per CTA, see gemm_persistent.cu; null in production
-};
+    const void* prefetch;         // optional: the NEXT GEMM's weight matrix; the (otherwise idle) epilogue warps pull it into L2
+    long long prefetch_bytes;     //   while this kernel's main loop runs -- a step touches 466 MB of weights, so without this
+};                                //   every GEMM starts on HBM misses (weights never survive in the 126 MB L2 until the next step)
 
 int gemm_pick_block_n(int N, bool ln);
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep, int block_n,

@@ -7,6 +7,7 @@
 // L2-resident row kernel (one warp per row, 16-byte coalesced accesses, two-pass fp32 statistics in registers) is
 // faster end to end.  Replaces BertSelfOutput / BertOutput / BertBiOutput `LayerNorm(dense(x) + residual)` and the
 // LayerNorm inside SimpleClassifier ([UPSTREAM] vilbert/vilbert.py; anchor /root/reference/worker.py:286-289).
+#include <cstdlib>
 #include "kernels.h"
 
 namespace vb {
@@ -77,7 +78,9 @@ cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long lo
     if (N % 128 != 0 || N / 128 > kLnMaxVec || (ld_y & 3) || (res && (ld_res & 3)) || (out_f32 && (ld_f32 & 3)) ||
         (out16 && (ld16 & 3)) || M < 1 || n_partials < 1 || (n_partials > 1 && (partial_stride & 3)))
         return cudaErrorInvalidValue;
-    const dim3 grid((M + 7) / 8), block(256);
+    // one warp per row; 2 rows per CTA: 992 CTAs for 1984 rows spread 7:6 over the 148 SMs (8 rows per CTA: 248 CTAs, 2:1)
+    static const int rows_per_cta = [] { const char* e = getenv("VB200_LN_ROWS"); const int v = e ? atoi(e) : 2; return (v >= 1 && v <= 8) ? v : 2; }();
+    const dim3 grid((M + rows_per_cta - 1) / rows_per_cta), block(32 * rows_per_cta);
     uint16_t* o16 = reinterpret_cast<uint16_t*>(out16);
 #define VB_LN(F, P) launch_ex(ln_residual_kernel<F, P>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, \
                             gamma, beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl)
