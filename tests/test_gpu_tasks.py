@@ -172,3 +172,25 @@ def test_retrieval_1000x1000_rank_block(full_oracle, engine, parity_log):
         worst = max(worst, abs(float(out[2].view(-1)[0]) - float(block[c, i])))
     parity_log(test="retrieval_1000x1000_rank_block", max_abs_err=worst, ref_std=float(block.std()))
     assert worst < 1e-2
+
+
+def test_prediction_batch_on_engine_is_exact(full_oracle, engine):
+    """Micro-batched requests (worker_api.prediction_batch: one forward for all of them, NLVR2 on even rows) decode to exactly
+    what one-request-at-a-time prediction() returns -- the engine's rows do not depend on their batch neighbours."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import worker_api as W
+    W.model = engine
+    W.label_maps.update(vqa=None, gqa=None)
+    reqs = []
+    for k, (task_id, n_img) in enumerate([("1", 1), ("12", 2), ("7", 3), ("11", 1), ("13", 1), ("15", 1), ("12", 2), ("4", 1)]):
+        inp = R.make_inputs(n_img, 37, 20, seed=300 + k)
+        reqs.append((inp[0][:1].cuda(), inp[1].cuda(), inp[2].cuda(), inp[3][:1].cuda(), inp[4][:1].cuda(), inp[5].cuda(),
+                     inp[6].cuda(), torch.tensor([[int(task_id)]]).cuda(), task_id,
+                     [{"image_width": 640, "image_height": 480}] * n_img))
+    single = [W.prediction(*r) for r in reqs]
+    got = W.prediction_batch(reqs)
+    for a, b in zip(got, single):
+        if isinstance(a, list):
+            assert a == b
+        else:
+            assert a["top3_answer"] == b["top3_answer"] and a["top3_confidence"] == b["top3_confidence"]

@@ -153,3 +153,112 @@ def test_shape_result():
     g = [{"x1": 1, "y1": 2, "x2": 3, "y2": 4, "confidence": 55.5555}] * 3
     assert W.shape_result("11", g, ["p"], ["n0", "n1", "n2"]) == {"task_id": "11", "image_name_list": ["n0", "n1", "n2"],
                                                                   "confidence_list": [55.56] * 3}
+
+
+# ----------------------------------------------------------------------------------------------- micro-batching
+class RowModel:
+    """Deterministic stand-in whose outputs for a row depend on that row only (as the real forward does), except the NLVR2
+    head, which consumes adjacent rows as one pair ([UPSTREAM] pooled.view(-1, 2048); worker.py:266-276)."""
+    _device = 0
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(11)
+        self.w = {k: torch.randn(2048 + 1, n, generator=g) for k, n in (("vqa", 3129), ("gqa", 1533), ("logit", 1), ("tri", 3),
+                                                                         ("bin", 2))}
+        self.wv = torch.randn(2048 + 5, generator=g)
+        self.calls = []
+
+    def __call__(self, question, features, spatials, segment_ids, input_mask, image_mask, co_mask, task_tokens,
+                 output_all_attention_masks=False, select=None):
+        B, V = features.shape[0], features.shape[1]
+        self.calls.append(dict(B=B, select=select))
+        x = torch.cat([features.float().mean(1), (question * input_mask).sum(1, keepdim=True).float() * 1e-3 +
+                       task_tokens.float()], dim=1)
+        vl = (torch.cat([features.float(), spatials.float()], dim=2) @ self.wv).unsqueeze(-1) + x[:, -1].view(B, 1, 1)
+        pair = (x.view(B // 2, 2, -1).sum(1) @ self.w["bin"]) if B % 2 == 0 else x @ self.w["bin"]
+        return (x @ self.w["vqa"], x @ self.w["gqa"], x @ self.w["logit"], pair, x @ self.w["tri"], None, vl, None,
+                torch.zeros(B, question.shape[1] + 1, 1), [])
+
+
+def _rand_req(task_id, n_img, V, seed, T=37):
+    g = torch.Generator().manual_seed(seed)
+    L_ = int(torch.randint(5, 20, (1,), generator=g))
+    q = torch.zeros(1, T, dtype=torch.long)
+    q[0, :L_] = torch.randint(1, 1000, (L_,), generator=g)
+    im = (q != 0).long()
+    return (q, torch.rand(n_img, V, 2048, generator=g), torch.rand(n_img, V, 5, generator=g), torch.zeros(1, T, dtype=torch.long),
+            im, torch.ones(n_img, V, dtype=torch.uint8), torch.zeros(n_img, V, T), torch.tensor([[int(task_id)]]), task_id,
+            [{"image_width": 640, "image_height": 480}] * n_img)
+
+
+def _same(a, b):
+    if isinstance(a, list):
+        assert [(x["x1"], x["y1"], x["x2"], x["y2"]) for x in a] == [(x["x1"], x["y1"], x["x2"], x["y2"]) for x in b]
+        assert [x["confidence"] for x in a] == pytest.approx([x["confidence"] for x in b], rel=1e-3)
+    else:                       # (the stub's CPU matmul rounds differently for different batch sizes; the engine does not)
+        assert a["top3_answer"] == b["top3_answer"]
+        assert a["top3_confidence"] == pytest.approx(b["top3_confidence"], rel=1e-3, abs=1e-6)
+
+
+def test_prediction_batch_equals_one_request_at_a_time():
+    W.label_maps.update(vqa=None, gqa=None)
+    reqs = [_rand_req("1", 1, 9, 1), _rand_req("12", 2, 9, 2),      # NLVR2 would start on row 1 -> filler row in front
+            _rand_req("7", 4, 9, 3), _rand_req("11", 1, 9, 4), _rand_req("13", 1, 9, 5), _rand_req("12", 2, 9, 6),
+            _rand_req("15", 1, 9, 7), _rand_req("1", 1, 21, 8),      # other region count -> its own model call
+            _rand_req("16", 1, 21, 9), _rand_req("12", 1, 9, 10)]    # invalid: NLVR2 with one image
+    W.model = RowModel()
+    single = []
+    for r in reqs[:-1]:
+        single.append(W.prediction(*r))
+    W.model = RowModel()
+    got = W.prediction_batch(reqs)
+    assert len(W.model.calls) == 2                                    # one per (T, V) group
+    assert sorted(c["B"] for c in W.model.calls) == [2, 14]          # 1 + filler + 2 + 4 + 1 + 1 + 2 + 1 = 13 -> even 14
+    big = max(W.model.calls, key=lambda c: c["B"])
+    assert big["select"] == (L.OUT_VIL_PREDICTION | L.OUT_VIL_BINARY_PREDICTION | L.OUT_VIL_LOGIT | L.OUT_VISION_LOGIT |
+                             L.OUT_VIL_TRI_PREDICTION | L.OUT_VIL_PREDICTION_GQA)
+    for a, b in zip(got[:-1], single):
+        _same(a, b)
+    assert isinstance(got[-1], AssertionError) and "2 images" in str(got[-1])
+
+
+def test_micro_batch_worker_round_trip():
+    """Messages in the sender's schema (demo/sender.py:19-24) go in, WebSocket result dicts (worker.py:564-649) come out, and
+    concurrent messages share a model call."""
+    W.label_maps.update(vqa=None, gqa=None)
+    W.model = RowModel()
+    W.tokenizer = W.WordpieceTokenizer(VOCAB)
+    g = torch.Generator().manual_seed(5)
+    boxes = np.array([[10, 20, 110, 220], [0, 0, 640, 480], [5, 5, 50, 40]], dtype=np.float32)
+
+    def det(n):
+        return ([torch.rand(3, 2048, generator=g) for _ in range(n)],
+                [{"image_width": 640, "image_height": 480, "bbox": boxes} for _ in range(n)])
+    msgs = [({"image_path": ["/m/demo/a.jpg"], "question": "what is the man holding?", "socket_id": "s1", "task_id": "1"}, *det(1)),
+            ({"image_path": ["/m/demo/a.jpg", "/m/demo/b.jpg"], "question": "the man is holding", "socket_id": "s2", "task_id": "12"}, *det(2)),
+            ({"image_path": ["/m/demo/a.jpg", "/m/demo/b.jpg", "/m/demo/c.jpg"], "question": "what color", "socket_id": "s3", "task_id": "7"}, *det(3)),
+            ({"image_path": ["/m/demo/a.jpg"], "question": "the man", "socket_id": "s4", "task_id": "11"}, *det(1)),
+            ({"image_path": ["/m/demo/a.jpg"], "question": "what", "socket_id": "s5", "task_id": "99"}, *det(1))]
+    expect = []
+    for body, feats, infos in msgs[:-1]:          # handle_request() with the tensors kept on the CPU (no GPU in this suite)
+        tid = body["task_id"]
+        args = W.build_inputs(body["question"], [int(tid)], feats, infos, torch.device("cpu"))
+        expect.append(W.shape_result(tid, W.prediction(*args, tid, infos), body["image_path"]))
+    W.model = RowModel()
+    worker = W.MicroBatchWorker(max_rows=64, max_wait_ms=300.0)
+    futs = [worker.submit(*m) for m in msgs]
+    res = [f.result(timeout=60) for f in futs[:-1]]
+    with pytest.raises(ValueError):
+        futs[-1].result(timeout=60)
+    worker.close()
+    assert [r["socket_id"] for r in res] == ["s1", "s2", "s3", "s4"]
+    for r, e in zip(res, expect):
+        assert r["result"]["task_id"] == e["task_id"]
+        if "result" in e:
+            assert [x["answer"] for x in r["result"]["result"]] == [x["answer"] for x in e["result"]]
+            assert [x["confidence"] for x in r["result"]["result"]] == pytest.approx([x["confidence"] for x in e["result"]], abs=0.02)
+        else:
+            assert r["result"]["image_name_list"] == e["image_name_list"]
+            assert r["result"]["confidence_list"] == pytest.approx(e["confidence_list"], abs=0.02)
+    # all five messages were pending together: ONE model call -- 1 + filler (NLVR2 onto an even row) + 2 + 3 + 1 rows
+    assert [c["B"] for c in W.model.calls] == [8]

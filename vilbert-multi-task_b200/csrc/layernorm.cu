@@ -14,7 +14,9 @@ namespace vb {
 
 constexpr int kLnMaxVec = 16;   // N <= 2048: float4 per lane per 128 columns
 
-template <bool F16, bool PARTIALS>
+// NV = float4 vectors per lane (N / 128): 6 for the 768-wide text stream, 8 for 1024; kLnMaxVec covers everything up to 2048
+// with run-time predication (the specialised forms carry a third of the instructions and registers).
+template <bool F16, bool PARTIALS, int NV>
 __global__ void __launch_bounds__(256)
 ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long long partial_stride,
                    const float* __restrict__ res, int ld_res,
@@ -24,13 +26,13 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
-    const int nvec = N >> 7;
+    const int nvec = NV < kLnMaxVec ? NV : (N >> 7);
     const float4* yp = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * ld_y);
     const float4* rp = res ? reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ld_res) : nullptr;
-    float4 x[kLnMaxVec];
+    float4 x[NV];
     float s = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
         if (k < nvec) {
             float4 a = yp[lane + 32 * k];
             if (PARTIALS) for (int sp = 1; sp < n_partials; ++sp) {          // split-K partial sums of the producing GEMM
@@ -46,7 +48,7 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
     const float mean = warp_sum(s) / static_cast<float>(N);
     float sq = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
         if (k < nvec) {
             const float a = x[k].x - mean, b = x[k].y - mean, c = x[k].z - mean, d = x[k].w - mean;
             sq += a * a + b * b + c * c + d * d;
@@ -58,7 +60,7 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
     float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * ld_f32) : nullptr;
     uint2* oh = out16 ? reinterpret_cast<uint2*>(out16 + static_cast<size_t>(row) * ld16) : nullptr;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
         if (k < nvec) {
             const float4 g = gp[lane + 32 * k], b = bp[lane + 32 * k];
             float4 o;
@@ -82,10 +84,12 @@ cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long lo
     static const int rows_per_cta = [] { const char* e = getenv("VB200_LN_ROWS"); const int v = e ? atoi(e) : 2; return (v >= 1 && v <= 8) ? v : 2; }();
     const dim3 grid((M + rows_per_cta - 1) / rows_per_cta), block(32 * rows_per_cta);
     uint16_t* o16 = reinterpret_cast<uint16_t*>(out16);
-#define VB_LN(F, P) launch_ex(ln_residual_kernel<F, P>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, ld_res, \
-                            gamma, beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl)
-    if (n_partials > 1) return f16 ? VB_LN(true, true) : VB_LN(false, true);
-    return f16 ? VB_LN(true, false) : VB_LN(false, false);
+#define VB_LN(F, P, V) launch_ex(ln_residual_kernel<F, P, V>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, \
+                               ld_res, gamma, beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl)
+    if (n_partials > 1) return f16 ? VB_LN(true, true, kLnMaxVec) : VB_LN(false, true, kLnMaxVec);
+    if (N == 768) return f16 ? VB_LN(true, false, 6) : VB_LN(false, false, 6);
+    if (N == 1024) return f16 ? VB_LN(true, false, 8) : VB_LN(false, false, 8);
+    return f16 ? VB_LN(true, false, kLnMaxVec) : VB_LN(false, false, kLnMaxVec);
 #undef VB_LN
 }
 

@@ -81,10 +81,8 @@ def _top(prob_1d: torch.Tensor, n: int):
     return val.tolist(), idx.tolist()
 
 
-def prediction(question, features, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_tokens,
-               task_id, infos):
-    """Validate, expand the text for pair / retrieval tasks, run the model once, decode.  worker.py:248-386."""
-    N = len(infos) if task_id == "7" else 3                      # worker.py:250-253
+def _validate(task_id, infos):
+    """Image-count rules of worker.py:255-262."""
     if task_id in SINGLE_IMAGE_TASKS:
         assert len(infos) == 1, "task require 1 image"
     elif task_id in PAIR_TASKS:
@@ -94,18 +92,21 @@ def prediction(question, features, spatials, segment_ids, input_mask, image_mask
     else:
         raise ValueError("task not valid.")
 
-    rep = 2 if task_id == "12" else (features.size(0) if task_id == "7" else 1)     # worker.py:266-284
-    if rep > 1:
-        question = question.repeat(rep, 1)
-        input_mask = input_mask.repeat(rep, 1)
-        segment_ids = segment_ids.repeat(rep, 1)
-        task_tokens = task_tokens.repeat(rep, 1)
 
-    out = model(question, features, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_tokens,
-                output_all_attention_masks=True, select=TASK_OUTPUT[task_id])
+def _expand_text(task_id, n_rows, question, input_mask, segment_ids, task_tokens):
+    """The text is repeated per image for NLVR2 pairs and retrieval candidates (worker.py:266-284)."""
+    rep = 2 if task_id == "12" else (n_rows if task_id == "7" else 1)
+    if rep > 1:
+        question, input_mask = question.repeat(rep, 1), input_mask.repeat(rep, 1)
+        segment_ids, task_tokens = segment_ids.repeat(rep, 1), task_tokens.repeat(rep, 1)
+    return question, input_mask, segment_ids, task_tokens
+
+
+def _decode(task_id, out, spatials, infos):
+    """Logits of ONE request -> the reference's answer (worker.py:295-386)."""
+    N = len(infos) if task_id == "7" else 3                      # worker.py:250-253
     (vil_prediction, vil_prediction_gqa, vil_logit, vil_binary_prediction, vil_tri_prediction, _vision_prediction,
      vision_logit, _linguisic_prediction, _linguisic_logit, _attn) = out
-
     if task_id in ("1", "2"):
         conf, idx = _top(torch.softmax(vil_prediction.view(-1), dim=0), N)
         return {"top3_answer": [_label("vqa", i) for i in idx], "top3_confidence": conf}
@@ -129,6 +130,66 @@ def prediction(question, features, spatials, segment_ids, input_mask, image_mask
     boxes = spatials[0][torch.as_tensor(idx, device=spatials.device)][:, :4].tolist()
     return [{"y1": int(b[1] * image_h), "y2": int(b[3] * image_h), "x1": int(b[0] * image_w), "x2": int(b[2] * image_w),
              "confidence": c * 100} for b, c in zip(boxes, conf)]
+
+
+def prediction(question, features, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_tokens,
+               task_id, infos):
+    """Validate, expand the text for pair / retrieval tasks, run the model once, decode.  worker.py:248-386."""
+    _validate(task_id, infos)
+    question, input_mask, segment_ids, task_tokens = _expand_text(task_id, features.size(0), question, input_mask,
+                                                                  segment_ids, task_tokens)
+    out = model(question, features, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_tokens,
+                output_all_attention_masks=True, select=TASK_OUTPUT[task_id])
+    return _decode(task_id, out, spatials, infos)
+
+
+def prediction_batch(requests):
+    """Micro-batching across requests (the reference handles one message at a time, worker.py:664-673).
+
+    `requests` is a list of argument tuples of `prediction()`.  Requests whose tensors have the same text length, region count
+    and feature width go through ONE model call; every pair's forward is independent of its batch neighbours, so each answer is
+    what `prediction()` returns for that request alone.  NLVR2 requests (task 12) are placed on even rows -- the binary head
+    consumes adjacent rows as one pair (worker.py:266-276) -- with a filler row in front when needed.  A request that fails
+    validation gets its exception as its answer; the others are unaffected."""
+    answers = [None] * len(requests)
+    groups = {}
+    for i, r in enumerate(requests):
+        (question, features, spatials, segment_ids, input_mask, image_mask, co_mask, task_tokens, task_id, infos) = r
+        try:
+            _validate(task_id, infos)
+        except (AssertionError, ValueError) as e:
+            answers[i] = e
+            continue
+        key = (question.shape[1], features.shape[1], features.shape[2])
+        groups.setdefault(key, []).append(i)
+    for idxs in groups.values():
+        rows, spans, select = [], {}, 0
+        n = 0
+        for i in idxs:
+            (question, features, spatials, segment_ids, input_mask, image_mask, co_mask, task_tokens, task_id, infos) = requests[i]
+            q, im, seg, tk = _expand_text(task_id, features.size(0), question, input_mask, segment_ids, task_tokens)
+            if task_id == "12" and n % 2 == 1:            # filler so that the pair starts on an even row
+                rows.append(rows[-1])
+                n += rows[-1][1].size(0)
+            if co_mask is None:
+                co_mask = torch.zeros(features.size(0), features.size(1), question.size(1), device=features.device)
+            rows.append((q, features, spatials, seg, im, image_mask, co_mask, tk))
+            spans[i] = (n, n + features.size(0))
+            n += features.size(0)
+            select |= TASK_OUTPUT[task_id]
+        if n % 2 == 1 and (select & L.OUT_VIL_BINARY_PREDICTION):
+            rows.append(tuple(t[-1:] for t in rows[-1]))   # the binary head needs an even number of rows
+            n += 1
+        cat = [torch.cat([r[k] for r in rows], dim=0) for k in range(8)]
+        out = model(*cat, output_all_attention_masks=True, select=select)
+        for i in idxs:
+            lo, hi = spans[i]
+            task_id, infos, spatials = requests[i][8], requests[i][9], requests[i][2]
+            sl = [None if o is None or isinstance(o, list) else o[lo:hi] for o in out[:9]] + [[]]
+            if out[3] is not None:
+                sl[3] = out[3][lo // 2:hi // 2] if task_id == "12" else out[3][0:0]
+            answers[i] = _decode(task_id, tuple(sl), spatials, infos)
+    return answers
 
 
 def build_inputs(query, task, features, infos, device, tok=None):
@@ -211,6 +272,90 @@ def handle_request(body: dict, features, infos):
 
 
 # ------------------------------------------------------------------------------------------ tokenizer
+class MicroBatchWorker(object):
+    """Dependency-light stand-in for the reference's consumer loop (`callback` / `main`, worker.py:542-673) with micro-batching.
+
+    `submit(body, features, infos)` takes the JSON message of demo/sender.py:19-24 (`image_path, question, socket_id, task_id`)
+    plus the detector output for its images (the detector itself, worker.py:59-223, is out of scope) and returns a
+    `concurrent.futures.Future` whose result is `{"socket_id": ..., "result": <the dict callback() pushes to the WebSocket,
+    worker.py:564-649>}`.  A background thread drains the queue: it waits at most `max_wait_ms` after the first pending message
+    for up to `max_rows` image rows, runs them through `prediction_batch` (one model call per shape group) and resolves the
+    futures; a failing request resolves to its exception, like the try/except of callback (worker.py:653-655)."""
+
+    def __init__(self, max_rows: int = 64, max_wait_ms: float = 2.0):
+        import queue
+        import threading
+        self.max_rows, self.max_wait = int(max_rows), float(max_wait_ms) * 1e-3
+        self._q = queue.Queue()
+        self._stop = False
+        self.batches = []                      # rows per model call group, for tests / monitoring
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def submit(self, body: dict, features, infos):
+        from concurrent.futures import Future
+        fut = Future()
+        self._q.put((body, features, infos, fut))
+        return fut
+
+    def close(self):
+        self._stop = True
+        self._q.put(None)
+        self._thread.join(timeout=10.0)
+
+    def _loop(self):
+        import queue
+        import time
+        while not self._stop:
+            item = self._q.get()
+            if item is None:
+                break
+            pending, rows = [item], len(item[2])
+            deadline = time.monotonic() + self.max_wait
+            while rows < self.max_rows:
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                try:
+                    nxt = self._q.get(timeout=left)
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._stop = True
+                    break
+                pending.append(nxt)
+                rows += len(nxt[2])
+            self._run(pending)
+
+    def _run(self, pending):
+        device = torch.device("cuda", model._device) if torch.cuda.is_available() else torch.device("cpu")
+        reqs, live = [], []
+        for body, features, infos, fut in pending:
+            try:
+                task_id = str(body["task_id"])
+                reqs.append(build_inputs(body["question"], [int(task_id)], features, infos, device) + (task_id, infos))
+                live.append((body, fut, task_id))
+            except Exception as e:             # noqa: BLE001 -- mirrors callback()'s catch-all (worker.py:653-655)
+                fut.set_exception(e)
+        if not reqs:
+            return
+        try:
+            answers = prediction_batch(reqs)
+        except Exception as e:                 # noqa: BLE001
+            for _, fut, _ in live:
+                fut.set_exception(e)
+            return
+        self.batches.append(sum(r[1].shape[0] for r in reqs))
+        for (body, fut, task_id), ans in zip(live, answers):
+            if isinstance(ans, Exception):
+                fut.set_exception(ans)
+            else:
+                try:
+                    fut.set_result({"socket_id": body.get("socket_id"), "result": shape_result(task_id, ans, body["image_path"])})
+                except Exception as e:         # noqa: BLE001
+                    fut.set_exception(e)
+
+
 class WordpieceTokenizer(object):
     """bert-base-uncased style tokenizer (lower-case, accent strip, punctuation split, greedy WordPiece) with the two
     methods the worker calls (worker.py:402-403).  Needs the user's vocab.txt: none ships with the reference."""
