@@ -271,3 +271,35 @@ def test_batch64_shard_equivalence(full_oracle, full_engines, parity_log):
     err = float((whole[idx].cpu() - ref).abs().max())
     parity_log(test="batch64_rows_vs_oracle", max_abs_err=err, ref_std=float(ref.std()))
     assert err < TOL
+
+
+def test_checkpoint_file_ingestion(tiny_oracle, tiny_engines, tmp_path):
+    """the worker's loading path (worker.py:470-536) -- config JSON file + torch-saved flat state_dict with the
+    DataParallel `module.` prefix and the tied/unused keys a real checkpoint carries -- gives the same engine as the in-memory
+    dict: identical outputs, bit for bit."""
+    import json
+    import vilbert_b200 as vb
+    cfg = tiny_oracle.config.to_dict()
+    cfg_path = tmp_path / "bert_base_6layer_6conect.json"
+    cfg_path.write_text(json.dumps(cfg))
+    sd = {"module." + k: v.clone() for k, v in tiny_oracle.state_dict().items()}
+    sd["module.cls.predictions.decoder.weight"] = sd["module.bert.embeddings.word_embeddings.weight"]     # tied copy
+    ckpt = tmp_path / "pytorch_model_9.bin"
+    torch.save(sd, ckpt)
+    # (worker_api.load_vilbert_model forces v_target_size = 1601 as worker.py:513 does, which only fits the full-size
+    # checkpoint; this reduced-width model goes through the same from_json_file / from_pretrained(path) calls directly)
+    config = vb.BertConfig.from_json_file(str(cfg_path))
+    m = vb.VILBertForVLTasks.from_pretrained(str(ckpt), config=config, num_labels=tiny_oracle.num_labels, default_gpu=True)
+    m.eval()
+    m.cuda(0)
+    dev = [t.cuda() for t in _tiny_inputs(tiny_oracle, 3, 20, 12, 77, pad=1)]
+    a = tiny_engines["fp16"](*dev, compute_pretraining_heads=True)
+    b = m(*dev, compute_pretraining_heads=True)
+    torch.cuda.synchronize()
+    for x, y in zip(a[:9], b[:9]):
+        assert torch.equal(x, y)
+    m.close()
+    sd.pop("module.bert.t_pooler.dense.bias")
+    torch.save(sd, ckpt)
+    with pytest.raises(RuntimeError, match="t_pooler.dense.bias"):
+        vb.VILBertForVLTasks.from_pretrained(str(ckpt), config=config, num_labels=tiny_oracle.num_labels).cuda(0)
