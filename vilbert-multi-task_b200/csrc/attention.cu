@@ -12,6 +12,7 @@
 // accumulate), additive key mask, online softmax with quad shuffles in fp32, P V again on mma.sync.
 // The co-attention kernel produces BOTH directions of a (sample, head) in one launch (text-query x image-key -> text
 // context, then image-query x text-key -> image context), re-using one Q/K/V buffer set so five CTAs fit per SM.
+#include <cstdlib>
 #include "kernels.h"
 
 namespace vb {
@@ -262,7 +263,8 @@ static cudaError_t launch_self(const __nv_bfloat16* qkv, int ld_qkv, int hidden,
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = set_smem(self_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    const int nwarps = min(8, (Lp / 16) * (D / 64));          // one warp per (16 query rows, 64 output columns) work item
+    static const int split_warps = [] { const char* e = getenv("VB200_ATTN_SPLIT_WARPS"); return e ? atoi(e) : 1; }();
+    const int nwarps = min(8, (Lp / 16) * (split_warps ? D / 64 : 1));   // one warp per (16 query rows, 64 output columns) work item
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv), ld_qkv, hidden, key_mask_add, reinterpret_cast<uint16_t*>(ctx),
@@ -292,7 +294,8 @@ static cudaError_t launch_co(const __nv_bfloat16* qkv_img, int ld_img, const __n
     if (smem > 227 * 1024) return cudaErrorInvalidValue;     // sequence too long for one CTA's shared memory
     cudaError_t e = set_smem(co_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    const int nwarps = max(4, min(8, (Lp / 16) * (D / 64)));  // >= 4 warps so the cp.async staging is spread over 128 threads
+    static const int split_warps = [] { const char* e = getenv("VB200_ATTN_SPLIT_WARPS"); return e ? atoi(e) : 1; }();
+    const int nwarps = max(4, min(8, (Lp / 16) * (split_warps ? D / 64 : 1)));  // >= 4 warps: cp.async staging over 128 threads
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv_img), ld_img, reinterpret_cast<const uint16_t*>(qkv_txt), ld_txt,

@@ -366,7 +366,12 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
-    bool weight_prefetch = true;    // VB200_PREFETCH=0 disables the L2 prefetch of the next GEMM's weights
+    // VB200_PDL=light: programmatic dependent launch only INTO the light kernels (LayerNorm, attention: no shared-memory slots
+    // to hog while they wait); GEMMs trigger after their main loop but are launched the normal way themselves.
+    bool pdl_light = false;
+    int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
+    bool weight_prefetch = false;   // VB200_PREFETCH=1: L2 prefetch of the next GEMM's weights from the idle epilogue warps
+                                    // (measured: 1.642 vs 1.629 ms per step -- the misses it hides are already overlapped)
     // CTA-pair GEMM (cta_group::2, gemm_pair.cu).  -1 = auto: 256-wide pair tiles where a GEMM has >= 4 waves of them (large
     // batches: +6 % at batch 512); below that the single-CTA kernel wins -- one or two tiles per CTA, where the pair's extra
     // cluster syncs and coarser tiles cost more than the halved W traffic saves (profiles/README.md).  VB200_PAIR=0|128|256
@@ -645,7 +650,7 @@ struct vb200_engine {
         op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.pair ? op.block_n / 2 : op.block_n, opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
-        e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = opt.use_pdl;
+        e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : opt.use_pdl;
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
         int split_k = 1;
         if (split_ln) {
@@ -881,17 +886,17 @@ struct vb200_engine {
                 break;
             case Op::SELF_ATTN:
                 CUDA_CHECK(vb::launch_self_attention(op.qkv_a, op.ld_a, op.hidden, op.mask_a, op.ctx_a, op.ld_ctx_a, op.B, op.La,
-                                                     op.heads, op.head_dim, opt.use_pdl, opt.act_fp16, st));
+                                                     op.heads, op.head_dim, light_pdl(), opt.act_fp16, st));
                 break;
             case Op::CO_ATTN:
                 CUDA_CHECK(vb::launch_co_attention(op.qkv_a, op.ld_a, op.qkv_b, op.ld_b, op.hidden, op.mask_a, op.mask_b, op.ctx_a,
                                                    op.ld_ctx_a, op.ctx_b, op.ld_ctx_b, op.B, op.La, op.Lb, op.heads, op.head_dim,
-                                                   opt.use_pdl, opt.act_fp16, st));
+                                                   light_pdl(), opt.act_fp16, st));
                 break;
             case Op::LAYERNORM:
                 CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.n_out > 1 ? op.n_out : 1, static_cast<long long>(op.ln_M) * op.ln_N,
                                                   op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
-                                                  op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, opt.use_pdl, st));
+                                                  op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, light_pdl(), st));
                 break;
             case Op::ROWDOT:
                 CUDA_CHECK(vb::launch_rowdot(op.x, op.ld_x, op.W, op.bias, op.add, op.out, op.ld_out, op.M, op.K, op.n_out, opt.use_pdl, st));
@@ -1103,7 +1108,8 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
-        if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "0") != 0);
+        if (const char* v = getenv("VB200_PDL")) eng->pdl_light = (strcmp(v, "light") == 0);
+        if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));

@@ -762,7 +762,7 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
-    fill_cfg<Cfg, LN>(cfg, attrs, grid, cluster, ep.pdl, st);
+    fill_cfg<Cfg, LN>(cfg, attrs, grid, cluster, ep.pdl == 1, st);
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, m_tiles, n_tiles);
 }
 

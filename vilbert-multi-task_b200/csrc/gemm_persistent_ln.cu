@@ -42,9 +42,11 @@ int gemm_p_pick_block_n(int N, bool ln) {
         if ((forced == 64 || forced == 128 || forced == 256) && N % forced == 0) return forced;
         return N <= 64 ? 64 : 128;
     }
-    static const int cands[5] = {128, 96, 192, 256, 64};
-    for (int ci = 0; ci < 5; ++ci) {
+    static const int first = [] { const char* e = getenv("VB200_LN_BN"); return e ? atoi(e) : 128; }();   // A/B: preferred width
+    const int cands[6] = {first, 128, 96, 192, 256, 64};
+    for (int ci = 0; ci < 6; ++ci) {
         const int bn = cands[ci];
+        if (bn != 64 && bn != 96 && bn != 128 && bn != 192 && bn != 256) continue;
         if (N % bn != 0 || N / bn > 8) continue;
         if (gemm_p_max_clusters(bn, N / bn) > 0) return bn;
     }

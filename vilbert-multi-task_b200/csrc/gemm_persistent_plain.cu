@@ -22,10 +22,11 @@ static cudaError_t dispatch_plain(const CUtensorMap& ta, const CUtensorMap& tb, 
     if constexpr (BN < 192) {
         // No more tiles than SMs: every CTA is alone on its SM -> deep ring, two MMA-issuing warps, 8 epilogue warps (PCfg::DEEP).
         // Timed alone that variant is 15-25 % faster for every such GEMM (profiles/README.md), but its 200 KB of shared memory
-        // keep the other stream's / the other in-flight batch's kernels off those SMs: with two batches in flight the step
-        // gets 6-12 % slower when the N = 768 / 1024 GEMMs use it.  Default: only the M <= 128 heads at the end of the step
-        // (nothing to overlap with there).  VB200_DEEP=0 never, =1 for every GEMM with <= #SM tiles.
-        static const int deep_mode = [] { const char* e = getenv("VB200_DEEP"); return e ? atoi(e) : 2; }();
+        // keep the other stream's / the other in-flight batch's kernels off those SMs (step 6-12 % slower with two batches in
+        // flight), and its two accumulator chains sum in a different order than the single-chain kernel, so a batch that
+        // crosses the tile-count threshold would no longer reproduce its shards bit for bit.  Opt-in only:
+        // VB200_DEEP=1 for every GEMM with <= #SM tiles, =2 for the M <= 128 heads only.
+        static const int deep_mode = [] { const char* e = getenv("VB200_DEEP"); return e ? atoi(e) : 0; }();
         const long long tiles = static_cast<long long>((ep.M + kBlockM - 1) / kBlockM) * ((ep.N + BN - 1) / BN) * (ep.split_k > 1 ? ep.split_k : 1);
         if (deep_mode != 0 && tiles <= num_sms() && (deep_mode == 1 || ep.M <= kBlockM))
             return dispatch_deep<BN>(ta, tb, ep, st);

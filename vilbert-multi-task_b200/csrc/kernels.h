@@ -22,7 +22,9 @@ struct GemmEpilogue {
     float* out_f32;               // optional
     int ld_f32;
     int act;
-    int pdl;                      // launched with programmatic stream serialization
+    int pdl;                      // in-kernel griddepcontrol.wait / launch_dependents; 1 = also LAUNCHED with programmatic stream
+                                  // serialization, 2 = trigger only (this GEMM waits for its predecessor the normal way, but
+                                  // lets a light dependent -- LayerNorm, attention -- start under its epilogue)
     int a_f16;                    // both GEMM operands (activations A, weights W) are fp16 instead of bf16
     int out_f16;                  // 16-bit output is fp16 instead of bf16
     int split_k;                  // plain kernel only: K is cut into split_k slices, slice s writes its fp32 partial sum to
