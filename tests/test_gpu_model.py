@@ -127,16 +127,19 @@ def test_tiny_model_eager_equals_graph(tiny_oracle, tiny_engines):
 
 
 def test_tiny_model_pdl(tiny_oracle, tiny_engines):
-    """Programmatic dependent launch changes scheduling only, never results."""
+    """Programmatic dependent launch changes scheduling only, never results: the default (into LayerNorm / attention kernels
+    only), every kernel (use_pdl=True) and none (use_pdl=False) agree bit for bit."""
     dev = [t.cuda() for t in _tiny_inputs(tiny_oracle, 2, 20, 12, 6)]
-    pdl = _engine(tiny_oracle, use_pdl=True)
-    a = tiny_engines["fp16"](*dev)
-    b = pdl(*dev)
-    torch.cuda.synchronize()
-    for x, y in zip(a[:9], b[:9]):
-        if x is not None:
-            assert torch.equal(x, y)
-    pdl.close()
+    a = tiny_engines["fp16"](*dev, compute_pretraining_heads=True)
+    for mode in (True, False):
+        other = _engine(tiny_oracle, use_pdl=mode)
+        for rep in range(3):
+            b = other(*dev, compute_pretraining_heads=True)
+            torch.cuda.synchronize()
+            for x, y in zip(a[:9], b[:9]):
+                if x is not None:
+                    assert torch.equal(x, y)
+        other.close()
 
 
 def test_tiny_model_fused_layernorm(tiny_oracle, tiny_engines, parity_log):

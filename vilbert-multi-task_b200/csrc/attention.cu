@@ -263,8 +263,10 @@ static cudaError_t launch_self(const __nv_bfloat16* qkv, int ld_qkv, int hidden,
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = set_smem(self_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    static const int split_warps = [] { const char* e = getenv("VB200_ATTN_SPLIT_WARPS"); return e ? atoi(e) : 1; }();
-    const int nwarps = min(8, (Lp / 16) * (split_warps ? D / 64 : 1));   // one warp per (16 query rows, 64 output columns) work item
+    static const int split_warps = [] { const char* e = getenv("VB200_ATTN_SPLIT_WARPS"); return e ? atoi(e) : 0; }();
+    // one warp per 16-row tile, walking its D / 64 column slices in turn (measured better than one warp per slice: 3-warp CTAs
+    // of the 128-wide heads fit five per SM -> one wave; VB200_ATTN_SPLIT_WARPS=1 for the other layout)
+    const int nwarps = min(8, (Lp / 16) * (split_warps ? D / 64 : 1));
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(self_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,
                      reinterpret_cast<const uint16_t*>(qkv), ld_qkv, hidden, key_mask_add, reinterpret_cast<uint16_t*>(ctx),
@@ -294,7 +296,7 @@ static cudaError_t launch_co(const __nv_bfloat16* qkv_img, int ld_img, const __n
     if (smem > 227 * 1024) return cudaErrorInvalidValue;     // sequence too long for one CTA's shared memory
     cudaError_t e = set_smem(co_attention_kernel<D, F16>, smem);
     if (e != cudaSuccess) return e;
-    static const int split_warps = [] { const char* e = getenv("VB200_ATTN_SPLIT_WARPS"); return e ? atoi(e) : 1; }();
+    static const int split_warps = [] { const char* e = getenv("VB200_ATTN_SPLIT_WARPS"); return e ? atoi(e) : 0; }();
     const int nwarps = max(4, min(8, (Lp / 16) * (split_warps ? D / 64 : 1)));  // >= 4 warps: cp.async staging over 128 threads
     const float scale_l2 = kLog2e / sqrtf(static_cast<float>(D));
     return launch_ex(co_attention_kernel<D, F16>, dim3(heads, B), dim3(32 * nwarps), smem, pdl, st,

@@ -366,9 +366,11 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
-    // VB200_PDL=light: programmatic dependent launch only INTO the light kernels (LayerNorm, attention: no shared-memory slots
-    // to hog while they wait); GEMMs trigger after their main loop but are launched the normal way themselves.
-    bool pdl_light = false;
+    // Programmatic dependent launch.  Default ("light"): only INTO the light kernels (LayerNorm, attention: no shared-memory
+    // slots to hog while they wait at griddepcontrol.wait); GEMMs trigger after their main loop but are themselves launched the
+    // normal way (+1.3 % throughput).  use_pdl > 0 / VB200_PDL=full: every kernel (faster with ONE batch in flight, slower with
+    // two: waiting GEMM CTAs sit on the second CTA slot of every SM).  use_pdl < 0 / VB200_PDL=off: none.
+    bool pdl_light = true;
     int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
     bool weight_prefetch = false;   // VB200_PREFETCH=1: L2 prefetch of the next GEMM's weights from the idle epilogue warps
                                     // (measured: 1.642 vs 1.629 ms per step -- the misses it hides are already overlapped)
@@ -1091,6 +1093,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         // tri-state flags: 0 = default, 1 = on, -1 = off
         o.use_cuda_graph = o.use_cuda_graph >= 0 ? 1 : 0;
         o.strict = o.strict >= 0 ? 1 : 0;
+        const int pdl_req = o.use_pdl;
         o.use_pdl = o.use_pdl > 0 ? 1 : 0;
         o.act_fp16 = o.act_fp16 >= 0 ? 1 : 0;
         o.fused_layernorm = o.fused_layernorm > 0 ? 1 : 0;
@@ -1108,7 +1111,12 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
-        if (const char* v = getenv("VB200_PDL")) eng->pdl_light = (strcmp(v, "light") == 0);
+        eng->pdl_light = pdl_req == 0;
+        if (const char* v = getenv("VB200_PDL")) {
+            eng->pdl_light = strcmp(v, "light") == 0;
+            if (strcmp(v, "full") == 0) eng->opt.use_pdl = 1;
+            if (strcmp(v, "off") == 0) eng->opt.use_pdl = 0;
+        }
         if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));

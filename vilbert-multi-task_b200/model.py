@@ -46,7 +46,7 @@ class VILBertForVLTasks(object):
     """Drop-in for ``vilbert.vilbert.VILBertForVLTasks`` on the inference path the worker uses."""
 
     def __init__(self, config: BertConfig, num_labels: int = 3129, state_dict=None, default_gpu: bool = True,
-                 use_cuda_graph: bool = True, use_pdl: bool = False, strict: bool = True, compute_dtype: str = "fp16",
+                 use_cuda_graph: bool = True, use_pdl: Optional[bool] = None, strict: bool = True, compute_dtype: str = "fp16",
                  fused_layernorm: bool = False):
         self.config = config
         self.num_labels = num_labels
@@ -137,7 +137,8 @@ class VILBertForVLTasks(object):
         opt.device = device
         opt.num_labels = int(self.num_labels or 0)
         opt.use_cuda_graph = 1 if self._opts["use_cuda_graph"] else -1
-        opt.use_pdl = 1 if self._opts["use_pdl"] else 0
+        # None: engine default (programmatic dependent launch into LayerNorm / attention only); True: every kernel; False: none
+        opt.use_pdl = 0 if self._opts["use_pdl"] is None else (1 if self._opts["use_pdl"] else -1)
         opt.strict = 1 if self._opts["strict"] else -1
         opt.act_fp16 = 1 if self._opts["compute_dtype"] == "fp16" else -1
         opt.fused_layernorm = 1 if self._opts["fused_layernorm"] else 0
