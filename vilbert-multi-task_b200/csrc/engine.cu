@@ -366,11 +366,14 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
-    // Programmatic dependent launch.  Default ("light"): only INTO the light kernels (LayerNorm, attention: no shared-memory
-    // slots to hog while they wait at griddepcontrol.wait); GEMMs trigger after their main loop but are themselves launched the
-    // normal way (+1.3 % throughput).  use_pdl > 0 / VB200_PDL=full: every kernel (faster with ONE batch in flight, slower with
-    // two: waiting GEMM CTAs sit on the second CTA slot of every SM).  use_pdl < 0 / VB200_PDL=off: none.
+    // Programmatic dependent launch.  Default ("medium"): INTO the light kernels (LayerNorm, attention: no shared-memory slots
+    // to hog while they wait at griddepcontrol.wait; GEMMs trigger after their main loop) and into a GEMM that directly follows
+    // a light kernel on its graph branch (see link_pdl) -- measured 1.557-1.566 ms per step vs 1.601-1.604 without.
+    // use_pdl > 0 / VB200_PDL=full: every kernel (faster with ONE batch in flight, slower with two: GEMM CTAs waiting for a
+    // whole predecessor GEMM sit on the second CTA slot of every SM).  VB200_PDL=light: light kernels only.
+    // use_pdl < 0 / VB200_PDL=off: none.
     bool pdl_light = true;
+    bool pdl_medium = true;
     int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
     bool weight_prefetch = false;   // VB200_PREFETCH=1: L2 prefetch of the next GEMM's weights from the idle epilogue warps
                                     // (measured: 1.642 vs 1.629 ms per step -- the misses it hides are already overlapped)
@@ -862,6 +865,7 @@ struct vb200_engine {
         for (Op& op : ops) if (op.kind == Op::ROWDOT) pl.flops += op.flops;
 
         link_prefetch(pl);
+        link_pdl(pl);
         // One eager pass first: opts kernels into their shared-memory sizes and surfaces launch-configuration
         // errors with a real message (errors inside a capture only invalidate the capture).
         {
@@ -974,6 +978,22 @@ struct vb200_engine {
         }
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     }
+    // PDL "medium" (default): additionally launch a GEMM programmatically when the kernel before it on its graph branch is a light one
+    // (LayerNorm / attention trigger their dependents right after loading their inputs, so the GEMM's prologue -- barrier init,
+    // TMEM allocation, descriptor prefetch -- overlaps the light kernel's math instead of following it).
+    void link_pdl(Plan& pl) {
+        if (!pdl_medium) return;
+        int prev_kind[2] = {-1, -1};
+        for (Op& op : pl.ops) {
+            const int st = op.stream & 1;
+            if (op.kind == Op::GEMM && op.ep.pdl == 2 &&
+                (prev_kind[st] == Op::LAYERNORM || prev_kind[st] == Op::SELF_ATTN || prev_kind[st] == Op::CO_ATTN))
+                op.ep.pdl = 1;
+            prev_kind[st] = op.kind;
+            if (op.sync != Op::NONE) prev_kind[0] = prev_kind[1] = -1;      // fork / join: the predecessor set is not one kernel
+        }
+    }
+
     // Every GEMM pulls the weights of the next GEMM of its graph branch into L2 while its own main loop runs (GemmEpilogue::
     // prefetch).  The last GEMM of a branch prefetches the first weights of the step (the next batch starts there).
     void link_prefetch(Plan& pl) {
@@ -1111,9 +1131,10 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
-        eng->pdl_light = pdl_req == 0;
+        eng->pdl_light = eng->pdl_medium = pdl_req == 0;
         if (const char* v = getenv("VB200_PDL")) {
-            eng->pdl_light = strcmp(v, "light") == 0;
+            eng->pdl_light = strcmp(v, "light") == 0 || strcmp(v, "medium") == 0;
+            eng->pdl_medium = strcmp(v, "medium") == 0;
             if (strcmp(v, "full") == 0) eng->opt.use_pdl = 1;
             if (strcmp(v, "off") == 0) eng->opt.use_pdl = 0;
         }
