@@ -374,6 +374,7 @@ struct vb200_engine {
     // use_pdl < 0 / VB200_PDL=off: none.
     bool pdl_light = true;
     bool pdl_medium = true;
+    bool early_w = true;            // VB200_EARLYW=0: no weight loads ahead of griddepcontrol.wait
     int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
     bool weight_prefetch = false;   // VB200_PREFETCH=1: L2 prefetch of the next GEMM's weights from the idle epilogue warps
                                     // (measured: 1.642 vs 1.629 ms per step -- the misses it hides are already overlapped)
@@ -988,7 +989,7 @@ struct vb200_engine {
             const int st = op.stream & 1;
             if (op.kind == Op::GEMM && op.ep.pdl == 2 &&
                 (prev_kind[st] == Op::LAYERNORM || prev_kind[st] == Op::SELF_ATTN || prev_kind[st] == Op::CO_ATTN))
-                op.ep.pdl = 1;
+                op.ep.pdl = early_w ? 5 : 1;
             prev_kind[st] = op.kind;
             if (op.sync != Op::NONE) prev_kind[0] = prev_kind[1] = -1;      // fork / join: the predecessor set is not one kernel
         }
@@ -1138,6 +1139,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
             if (strcmp(v, "full") == 0) eng->opt.use_pdl = 1;
             if (strcmp(v, "off") == 0) eng->opt.use_pdl = 0;
         }
+        if (const char* v = getenv("VB200_EARLYW")) eng->early_w = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));

@@ -357,7 +357,7 @@ static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, con
     attrs[na].val.clusterDim.y = 1;
     attrs[na].val.clusterDim.z = 1;
     ++na;
-    if (ep.pdl == 1) {
+    if (ep.pdl == 1 || ep.pdl == 5) {
         attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;

@@ -409,15 +409,32 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (stamps && threadIdx.x == 0) stamps[1] = clock64();
 
-    if (p.pdl) {
-        pdl_wait();       // everything above overlapped the previous kernel's tail; its outputs are visible from here on
-    }
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The producer thread goes further:
+    // the weight tiles (W) do not depend on the previous kernel, so it puts the W loads of the first ring pass in flight
+    // BEFORE griddepcontrol.wait and only the activation tiles (A) after it.
+    const bool early_w = p.pdl == 5 && !LN;            // 5 = launched programmatically + early weight loads (kernels.h)
+    if (p.pdl && !(early_w && threadIdx.x == 0)) pdl_wait();
 
     if (warp == 0) {
         // ============================================================ TMA producer
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
+            int early = 0;                                     // k-blocks of the first tile whose W tile is already in flight
+            if (early_w) {
+                if (first_tile < total_tiles) {
+                    const int mn = first_tile / split_k, ks = first_tile % split_k;
+                    const int n0 = (mn % num_n_tiles) * BLOCK_N;
+                    const int kb0 = ks * kbs, kb_end = min(num_kb, (ks + 1) * kbs);
+                    early = min(kStages, kb_end - kb0);
+                    for (int i = 0; i < early; ++i) {          // fresh barriers: every slot is free
+                        uint8_t* sb = ring + i * Cfg::kStageBytes + Cfg::kStageBytesA;
+                        mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
+                        tma_load_2d(sb, &tmap_b, &full_bar[i], (kb0 + i) * kBlockK, n0);
+                    }
+                }
+                pdl_wait();                                    // the previous kernel's outputs (A) are visible from here on
+            }
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
                 const int mn = LN ? tile : tile / split_k;
                 const int ks = LN ? 0 : tile % split_k;
@@ -425,12 +442,17 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const int n0 = (LN ? static_cast<int>(my_rank) : mn % num_n_tiles) * BLOCK_N;
                 const int kb_end = min(num_kb, (ks + 1) * kbs);
                 for (int kb = ks * kbs; kb < kb_end; ++kb) {
-                    mbar_wait(&empty_bar[s], phase ^ 1u);
                     uint8_t* sa = ring + s * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kStageBytesA;
-                    mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                    tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
-                    tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0);
+                    if (early > 0) {                           // first ring pass of the first tile: W is already on its way
+                        --early;
+                        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+                    } else {
+                        mbar_wait(&empty_bar[s], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+                        tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0);
+                    }
                     if (++s == kStages) { s = 0; phase ^= 1u; }
                 }
             }
@@ -762,7 +784,7 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
-    fill_cfg<Cfg, LN>(cfg, attrs, grid, cluster, ep.pdl == 1, st);
+    fill_cfg<Cfg, LN>(cfg, attrs, grid, cluster, ep.pdl == 1 || ep.pdl == 5, st);
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, m_tiles, n_tiles);
 }
 

@@ -24,7 +24,9 @@ struct GemmEpilogue {
     int act;
     int pdl;                      // in-kernel griddepcontrol.wait / launch_dependents; 1 = also LAUNCHED with programmatic stream
                                   // serialization, 2 = trigger only (this GEMM waits for its predecessor the normal way, but
-                                  // lets a light dependent -- LayerNorm, attention -- start under its epilogue)
+                                  // lets a light dependent -- LayerNorm, attention -- start under its epilogue),
+                                  // 5 = as 1, and the producer puts the first ring pass of WEIGHT tiles in flight before
+                                  // griddepcontrol.wait (weights do not depend on the previous kernel)
     int a_f16;                    // both GEMM operands (activations A, weights W) are fp16 instead of bf16
     int out_f16;                  // 16-bit output is fp16 instead of bf16
     int split_k;                  // plain kernel only: K is cut into split_k slices, slice s writes its fp32 partial sum to
