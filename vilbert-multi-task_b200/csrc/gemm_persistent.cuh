@@ -6,8 +6,13 @@
 //     of tile i+1, and the accumulator is handed back as soon as it has been read into registers;
 //   * epilogue code is specialised OUTSIDE the per-element loops (activation, 16-bit format) -- measured: per-element
 //     run-time branches made a bias-only epilogue cost 11 k cycles per 128x128 tile, 4x the MMA time;
-//   * the fp32 residual of the next 32-column chunk is prefetched while the current chunk is processed, and the first
-//     chunk's residual is requested before the accumulator is even ready;
+//   * eight epilogue warps (two per SM sub-partition), every staging access a true LDS/STS, outputs transposed through a
+//     swizzled 2 KB per-warp buffer so that a store instruction writes 8 rows x 64 bytes, GELU through a 15-slot polynomial
+//     erf -- together 10 % of the whole step (profiles/r1_mma_issue_rate.txt, section 8);
+//   * launched programmatically (GemmEpilogue::pdl) the producer issues the weight tiles of the first ring pass before
+//     griddepcontrol.wait; every kernel triggers its dependents once its last MMA is issued;
+//   * LN variant: the fp32 residual of the next 32-column chunk is prefetched while the current chunk is processed, and the
+//     first chunk's residual is requested before the accumulator is even ready;
 //   * LayerNorm (8 epilogue warps, x kept in registers, TMEM read once) exchanges ONE (mean, M2) pair per row, column
 //     half and CTA through distributed shared memory (Chan's parallel variance), synchronised by cluster-scope
 //     mbarriers that only the epilogue warps touch -- producer and MMA warps are never stalled by the normalisation.
@@ -25,8 +30,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 
-// EPI8: eight epilogue warps (two column groups per TMEM lane quarter).  LayerNorm tiles, GELU tiles (the erf costs ~16
-// instructions per element: with four warps the epilogue of a 128x128 tile took 11 k cycles, 3.5x its MMA time) and 256-wide tiles.
+// EPI8: eight epilogue warps (two column groups per TMEM lane quarter) -- every instantiation uses it now (KCfg); with four,
+// each SM sub-partition ran ONE epilogue warp and every dependent instruction paid its full latency.
 template <int BLOCK_N, bool LN, bool EPI8 = LN, bool DEEP = false>
 struct PCfg {
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
@@ -48,9 +53,7 @@ struct PCfg {
     static constexpr int kMinBlocks = (LN || BLOCK_N >= 192 || DEEP) ? 1 : 2;
     // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
     // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
-    //   plain: 32 rows x 20 words of packed 16-bit pairs;  LN: 32 rows x 33 fp32 (serves the fp32 and the 16-bit output)
-    //   plain, 8 warps, two CTAs per SM: only 32 x 12 words fit (16-bit outputs, 16 columns at a time; fp32 falls back to
-    //   per-lane stores -- that combination only occurs for the 64-row classifier heads)
+    //   plain: 32 rows x 64 bytes, XOR-swizzled (store16_sw / store_f32_sw);  LN: 32 rows x 33 fp32
     static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 2048;      // plain: 32 rows x 64 B, swizzled (store16_sw)
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
@@ -69,9 +72,9 @@ struct PCfg {
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
     // LN: chunks per epilogue thread (two column halves per TMEM lane quarter)
     static constexpr int kCPT = (kNumChunks + 1) / 2;
-    // ring | bias[2][BLOCK_N] gamma beta (4*BLOCK_N f32) | part[2 bufs][2 halves][128] float2 | barriers | tmem ptr
+    // ring | bias (LN: + gamma beta) | LN: part[2 bufs][2 halves][128] float2 | barriers | tmem ptr | transpose buffers
     static constexpr int kNumBars = 2 * kStages + 4 + 2;
-    // LN-only pieces (gamma, beta, cluster partials) cost nothing in the plain kernel, whose budget is (227 KB - 2 KB) / 2
+    // LN-only pieces (gamma, beta, cluster partials) cost nothing in the plain kernel, whose budget is 233472 / 2 - 1024
     static constexpr int kLnAux = LN ? 2 * BLOCK_N * 4 + 4 * kBlockM * 8 : 0;
     // plain: ONE bias slice (the tile-end barrier of the epilogue warps protects it); LN keeps bias | gamma | beta resident
     static constexpr int kBiasFloats = LN ? 2 * BLOCK_N : BLOCK_N;
