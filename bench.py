@@ -40,7 +40,8 @@ def parse():
     p.add_argument("--rotate", type=int, default=8, help="distinct resident input batches cycled through (L2 defeat)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
-    p.add_argument("--pdl", action="store_true")
+    p.add_argument("--pdl", choices=["default", "on", "off"], default="default",
+                   help="programmatic dependent launch: engine default (every kernel), forced on, or off")
     p.add_argument("--all-heads", action="store_true", help="compute the seven task heads instead of VQA only")
     p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
                    help="16-bit format of the tensor-core operands (same tcgen05 rate; fp16 is the engine default, see DESIGN.md 2)")
@@ -181,7 +182,7 @@ def run_b200(args):
     cfg = vb.BertConfig(task_specific_tokens=True, visualization=True)       # worker.py:509-522
     sd = S.synthetic_state_dict(cfg, seed=42)
     model = vb.VILBertForVLTasks.from_pretrained(sd, config=cfg, num_labels=3129, use_cuda_graph=not args.no_graph,
-                                                 use_pdl=args.pdl, compute_dtype=args.dtype,
+                                                 use_pdl={"default": None, "on": True, "off": False}[args.pdl], compute_dtype=args.dtype,
                                                  fused_layernorm=args.fused_ln).eval().cuda(local_rank)
     select = L.OUT_TASK_HEADS if args.all_heads else L.OUT_VIL_PREDICTION
     n_launch, flops = model.plan_info(B, Tin, V, select)
@@ -323,7 +324,7 @@ def run_b200(args):
                        "l2": f"inputs rotate over {args.rotate} resident batches ({args.rotate * in_bytes / 1e6:.0f} MB) "
                              f"+ {model._dims['weight_bytes'] / 1e6:.0f} MB of weights > 126 MB L2",
                        "batches_in_flight": nfl,
-                       "cuda_graph": not args.no_graph, "pdl": bool(args.pdl), "layernorm": "fused" if args.fused_ln else "split",
+                       "cuda_graph": not args.no_graph, "pdl": "every kernel" if args.pdl != "off" else "off", "layernorm": "fused" if args.fused_ln else "split",
                        "heads": "task heads" if args.all_heads else "vil_prediction"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps},

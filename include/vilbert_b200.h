@@ -107,8 +107,7 @@ typedef struct {
     int32_t device;                /* CUDA ordinal */
     int32_t num_labels;            /* vil_prediction width; 0 -> taken from the checkpoint (worker.py:523: 3129) */
     int32_t use_cuda_graph;        /* default on: each (B,Tin,V,select) plan is captured once and replayed */
-    int32_t use_pdl;               /* programmatic dependent launch: 0 default (into LayerNorm / attention kernels and
-                                      into the GEMM that follows one), > 0 every kernel, < 0 none */
+    int32_t use_pdl;               /* programmatic dependent launch: 0 default (= every kernel), > 0 every kernel, < 0 none */
     int32_t strict;                /* default on: unexpected checkpoint keys are an error */
     int32_t act_fp16;              /* 16-bit format of the tensor-core operands (weights AND activations; tcgen05 kind::f16
                                       needs matching A/B formats).  default on: IEEE fp16 (11-bit significand; activations

@@ -12,6 +12,6 @@ except Exception as e:
 PY
 }
 run base timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline
-run pdl timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --pdl
+run pdl timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --pdl on
 run b512auto timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --batch 512
 run b256auto timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --batch 256

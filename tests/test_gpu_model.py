@@ -127,8 +127,8 @@ def test_tiny_model_eager_equals_graph(tiny_oracle, tiny_engines):
 
 
 def test_tiny_model_pdl(tiny_oracle, tiny_engines):
-    """Programmatic dependent launch changes scheduling only, never results: the default (into LayerNorm / attention kernels
-    only), every kernel (use_pdl=True) and none (use_pdl=False) agree bit for bit."""
+    """Programmatic dependent launch changes scheduling only, never results: the default (every kernel), forced on
+    (use_pdl=True) and none (use_pdl=False) agree bit for bit."""
     dev = [t.cuda() for t in _tiny_inputs(tiny_oracle, 2, 20, 12, 6)]
     a = tiny_engines["fp16"](*dev, compute_pretraining_heads=True)
     for mode in (True, False):

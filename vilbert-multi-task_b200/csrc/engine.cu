@@ -366,15 +366,16 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
-    // Programmatic dependent launch.  Default ("medium"): INTO the light kernels (LayerNorm, attention: no shared-memory slots
-    // to hog while they wait at griddepcontrol.wait; GEMMs trigger after their main loop) and into a GEMM that directly follows
-    // a light kernel on its graph branch (see link_pdl) -- measured 1.557-1.566 ms per step vs 1.601-1.604 without.
-    // use_pdl > 0 / VB200_PDL=full: every kernel (faster with ONE batch in flight, slower with two: GEMM CTAs waiting for a
-    // whole predecessor GEMM sit on the second CTA slot of every SM).  VB200_PDL=light: light kernels only.
-    // use_pdl < 0 / VB200_PDL=off: none.
+    // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
+    // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
+    // batches in flight, per step: off 1.597-1.604 ms | full 1.567 | "mediumplus" (everything except edges across a fork / join)
+    // 1.571-1.581 | "medium" (into LayerNorm / attention and into the GEMM that follows one) 1.557-1.566 on another box whose
+    // off was 1.601; with ONE batch in flight 1.83 (full) vs 1.96 ms (off).
+    // VB200_PDL=off|light|medium|mediumplus|full; use_pdl < 0 = off, > 0 = full.
     bool pdl_light = true;
     bool pdl_medium = true;
     bool early_w = true;            // VB200_EARLYW=0: no weight loads ahead of griddepcontrol.wait
+    bool pdl_gemm_gemm = false;     // VB200_PDL=mediumplus: also GEMM -> GEMM edges of one graph branch (FFN-in -> FFN-out)
     int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
     bool weight_prefetch = false;   // VB200_PREFETCH=1: L2 prefetch of the next GEMM's weights from the idle epilogue warps
                                     // (measured: 1.642 vs 1.629 ms per step -- the misses it hides are already overlapped)
@@ -656,7 +657,7 @@ struct vb200_engine {
         op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.pair ? op.block_n / 2 : op.block_n, opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
-        e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : opt.use_pdl;
+        e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : (opt.use_pdl ? (early_w ? 5 : 1) : 0);
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
         int split_k = 1;
         if (split_ln) {
@@ -988,7 +989,8 @@ struct vb200_engine {
         for (Op& op : pl.ops) {
             const int st = op.stream & 1;
             if (op.kind == Op::GEMM && op.ep.pdl == 2 &&
-                (prev_kind[st] == Op::LAYERNORM || prev_kind[st] == Op::SELF_ATTN || prev_kind[st] == Op::CO_ATTN))
+                (prev_kind[st] == Op::LAYERNORM || prev_kind[st] == Op::SELF_ATTN || prev_kind[st] == Op::CO_ATTN ||
+                 (pdl_gemm_gemm && prev_kind[st] == Op::GEMM)))
                 op.ep.pdl = early_w ? 5 : 1;
             prev_kind[st] = op.kind;
             if (op.sync != Op::NONE) prev_kind[0] = prev_kind[1] = -1;      // fork / join: the predecessor set is not one kernel
@@ -1132,10 +1134,12 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
-        eng->pdl_light = eng->pdl_medium = pdl_req == 0;
+        eng->pdl_light = eng->pdl_medium = false;
+        if (pdl_req == 0) eng->opt.use_pdl = 1;               // default: full
         if (const char* v = getenv("VB200_PDL")) {
-            eng->pdl_light = strcmp(v, "light") == 0 || strcmp(v, "medium") == 0;
-            eng->pdl_medium = strcmp(v, "medium") == 0;
+            eng->pdl_gemm_gemm = strcmp(v, "mediumplus") == 0;
+            eng->pdl_light = strcmp(v, "light") == 0 || strcmp(v, "medium") == 0 || eng->pdl_gemm_gemm;
+            eng->pdl_medium = strcmp(v, "medium") == 0 || eng->pdl_gemm_gemm;
             if (strcmp(v, "full") == 0) eng->opt.use_pdl = 1;
             if (strcmp(v, "off") == 0) eng->opt.use_pdl = 0;
         }
