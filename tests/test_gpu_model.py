@@ -103,11 +103,13 @@ def _tiny_inputs(oracle, B, Tin, V, seed, pad=0):
     return inp
 
 
-@pytest.mark.parametrize("B,Tin,V,pad", [(2, 30, 36, 0), (3, 16, 10, 3), (4, 37, 101, 7), (1, 12, 37, 0), (2, 128, 100, 0)])
+@pytest.mark.parametrize("B,Tin,V,pad", [(2, 30, 36, 0), (3, 16, 10, 3), (4, 37, 101, 7), (1, 12, 37, 0), (2, 128, 100, 0),
+                                         (1, 3, 1, 0), (1, 155, 256, 11), (5, 3, 7, 2)])
 def test_tiny_model_all_outputs(tiny_oracle, tiny_engines, parity_log, B, Tin, V, pad):
     """Structurally complete 12/6/6 model at reduced width: all nine outputs incl. the pre-training heads, ragged text
     lengths, masked regions, odd batch (binary head falls back to the seq-relationship score), and the corner of the
-    BASELINE sweep (text 128, regions 100)."""
+    BASELINE sweep (text 128, regions 100); extremes: three tokens ([CLS] id [SEP]) + one region, 155 tokens (the tiny model has 160 positions)
+    x 256 regions (four key blocks in every attention kernel), an odd batch of tiny sequences."""
     _check(tiny_oracle, tiny_engines, _tiny_inputs(tiny_oracle, B, Tin, V, 100 + B, pad), parity_log,
            f"tiny_B{B}_T{Tin}_V{V}", pretraining=True)
 

@@ -182,7 +182,7 @@ def _attn_ref(q, k, v, mask_add, heads):
 
 @pytest.mark.parametrize("act_dt", ACT)
 @pytest.mark.parametrize("B,L,heads,d", [(3, 31, 12, 64), (2, 38, 12, 64), (2, 36, 8, 128), (2, 101, 8, 128),
-                                         (1, 129, 2, 64), (2, 17, 2, 128)])
+                                         (1, 129, 2, 64), (2, 17, 2, 128), (1, 256, 2, 128), (2, 1, 2, 64), (1, 2, 1, 128)])
 def test_self_attention(B, L, heads, d, act_dt, parity_log):
     Lm, lib = _lib()
     H = heads * d
@@ -205,7 +205,7 @@ def test_self_attention(B, L, heads, d, act_dt, parity_log):
 
 @pytest.mark.parametrize("act_dt", ACT)
 @pytest.mark.parametrize("B,T,V,heads,d", [(3, 31, 36, 8, 128), (2, 38, 101, 8, 128), (2, 17, 10, 2, 128),
-                                           (1, 129, 100, 8, 128)])
+                                           (1, 129, 100, 8, 128), (1, 256, 256, 2, 128), (2, 2, 1, 2, 128), (1, 1, 200, 1, 64)])
 def test_co_attention(B, T, V, heads, d, act_dt, parity_log):
     Lm, lib = _lib()
     H = heads * d
