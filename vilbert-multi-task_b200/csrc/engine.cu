@@ -293,12 +293,38 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
     return m;
 }
 
+// Output tile map for the TMA-store epilogue: [rows, cols] row-major with leading dimension ld (elements), boxes of 128 rows x
+// 128 bytes (64 16-bit or 32 fp32 columns), SWIZZLE_128B.  Returns false when the buffer does not meet the TMA's alignment rules.
+bool make_tmap_out(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, bool fp32, bool f16) {
+    const int esz = fp32 ? 4 : 2;
+    if (base == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) || (ld * esz) % 16 != 0 || rows < 1 || cols < 1) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), 128};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                        : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    return get_encode_fn()(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// Decide whether a plain GEMM may use the TMA-store epilogue and build its output map (exactly one output, aligned).
+void setup_tma_store(CUtensorMap* tc, GemmEpilogue& e) {
+    e.tma_store = 0;
+    if (e.split_k > 1 || e.gamma != nullptr) return;
+    if (e.out_bf16 != nullptr && e.out_f32 == nullptr) {
+        if (make_tmap_out(tc, e.out_bf16, e.M, e.N, e.ld_bf16, false, e.out_f16 != 0)) e.tma_store = 1;
+    } else if (e.out_f32 != nullptr && e.out_bf16 == nullptr) {
+        if (make_tmap_out(tc, e.out_f32, e.M, e.N, e.ld_f32, true, false)) e.tma_store = 2;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ launch list
 struct Op {
     enum Kind { GEMM, SELF_ATTN, CO_ATTN, ROWDOT, LAYERNORM } kind;
     int stream = 0;                // 0 main, 1 side (image branch) inside the captured graph
     // GEMM
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc;        // operands, and the output (TMA-store epilogue, ep.tma_store != 0)
     GemmEpilogue ep;
     int block_n = 128;
     bool ln = false;
@@ -374,6 +400,7 @@ struct vb200_engine {
     // VB200_PDL=off|light|medium|mediumplus|full; use_pdl < 0 = off, > 0 = full.
     bool pdl_light = true;
     bool pdl_medium = true;
+    bool tma_store_enabled = true;  // VB200_TMASTORE=0: every tile leaves through the register / LSU epilogue
     bool early_w = true;            // VB200_EARLYW=0: no weight loads ahead of griddepcontrol.wait
     bool pdl_gemm_gemm = false;     // VB200_PDL=mediumplus: also GEMM -> GEMM edges of one graph branch (FFN-in -> FFN-out)
     int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
@@ -682,6 +709,7 @@ struct vb200_engine {
             e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr;
             e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f;
         }
+        if (tma_store_enabled && !gemm_v1 && !op.pair && !op.ln) setup_tma_store(&op.tc, e);
         op.flops = 2.0 * a_rows * W.N * W.K;
         op.w = W.w;
         op.w_bytes = static_cast<long long>(W.N) * W.ldw * 2;
@@ -890,7 +918,11 @@ struct vb200_engine {
             case Op::GEMM:
                 if (gemm_v1) CUDA_CHECK(vb::launch_gemm(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
                 else if (op.pair) CUDA_CHECK(vb::launch_gemm_pair(op.ta, op.tb, op.ep, op.block_n, st));
-                else CUDA_CHECK(vb::launch_gemm_persistent(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
+                else {
+                    GemmEpilogue e = op.ep;
+                    e.tmap_c_host = e.tma_store ? &op.tc : nullptr;       // Op objects move when the list grows: bind here
+                    CUDA_CHECK(vb::launch_gemm_persistent(op.ta, op.tb, e, op.block_n, op.ln, st));
+                }
                 break;
             case Op::SELF_ATTN:
                 CUDA_CHECK(vb::launch_self_attention(op.qkv_a, op.ld_a, op.hidden, op.mask_a, op.ctx_a, op.ld_ctx_a, op.B, op.La,
@@ -1143,6 +1175,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
             if (strcmp(v, "full") == 0) eng->opt.use_pdl = 1;
             if (strcmp(v, "off") == 0) eng->opt.use_pdl = 0;
         }
+        if (const char* v = getenv("VB200_TMASTORE")) eng->tma_store_enabled = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_EARLYW")) eng->early_w = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
@@ -1299,6 +1332,9 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
         e.gamma = gamma; e.beta = beta; e.eps = eps; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = (int)ld_y_bf16;
         e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.pdl = use_pdl;
         e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16; e.timing = timing;
+        CUtensorMap tc;
+        const char* ts = getenv("VB200_TMASTORE");
+        if (variant == 0 && !ln && !(ts && strcmp(ts, "0") == 0)) { setup_tma_store(&tc, e); e.tmap_c_host = e.tma_store ? &tc : nullptr; }
         if (variant == 1) CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
         else if (pair) CUDA_CHECK(vb::launch_gemm_pair(ta, tb, e, bn, static_cast<cudaStream_t>(cuda_stream)));
         else CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));

@@ -329,7 +329,8 @@ struct KCfg { using type = PCfg<BLOCK_N, LN, true, DEEP>; };   // 8 epilogue war
 template <int BLOCK_N, bool LN, int ACT, bool F16, bool DEEP = false>
 __global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT, DEEP>::type::kThreads, KCfg<BLOCK_N, LN, ACT, DEEP>::type::kMinBlocks)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const GemmEpilogue p, const int num_m_tiles, const int num_n_tiles) {
+                       const __grid_constant__ CUtensorMap tmap_c, const GemmEpilogue p, const int num_m_tiles,
+                       const int num_n_tiles) {
     using Cfg = typename KCfg<BLOCK_N, LN, ACT, DEEP>::type;
     constexpr int kStages = Cfg::kStages;
     constexpr int kNC = Cfg::kNumChunks;
@@ -386,6 +387,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (!LN && p.tma_store) tma_prefetch_desc(&tmap_c);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -543,12 +545,43 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tc_fence_after();
                 if (stamp) stamps[4] = clock64();
                 float* const out_f32 = p.out_f32 ? p.out_f32 + static_cast<long long>(ks) * p.split_stride : nullptr;   // split-K slice
+                // TMA-store path (CTA-uniform): this is the CTA's last tile, so no operand load is or will be in flight and
+                // every MMA that read the ring has completed (tmem_full above)
+                const bool use_tma = p.tma_store != 0 && st_fast && tile + tile_stride >= total_tiles &&
+                                     (p.tma_store == 1 ? (p.out_bf16 != nullptr && p.out_f32 == nullptr)
+                                                       : (p.out_f32 != nullptr && p.out_bf16 == nullptr));
                 auto finish_chunk = [&](float (&v)[32], int nc) {
                     bias_act32<ACT>(v, bias_t + (nc - n0));
                     if (p.mul != nullptr && m_ok) {
                         const float* mp = p.mul + static_cast<size_t>(m) * p.ld_mul + nc;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
+                    }
+                    if (use_tma) {
+                        // last tile of this CTA: the operand ring is idle -> stage the tile there in the TMA's SWIZZLE_128B
+                        // layout (16-byte unit u of row r at u ^ (r & 7): row-per-lane writes are bank-conflict free)
+                        const int cl = nc - n0;
+                        if (p.tma_store == 1) {                              // 16-bit: slabs of 64 columns x 128 rows (16 KB)
+                            uint4* slab = reinterpret_cast<uint4*>(ring + (cl >> 6) * (kBlockM * 128)) + row * 8;
+                            const int u0 = (cl & 32) ? 4 : 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                u.x = F16 ? pack16x2_rt(v[8 * j + 0], v[8 * j + 1], 1) : pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                                u.y = F16 ? pack16x2_rt(v[8 * j + 2], v[8 * j + 3], 1) : pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                                u.z = F16 ? pack16x2_rt(v[8 * j + 4], v[8 * j + 5], 1) : pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                                u.w = F16 ? pack16x2_rt(v[8 * j + 6], v[8 * j + 7], 1) : pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                slab[(u0 + j) ^ (row & 7)] = u;
+                            }
+                        } else {                                             // fp32: slabs of 32 columns x 128 rows (16 KB)
+                            uint4* slab = reinterpret_cast<uint4*>(ring + (cl >> 5) * (kBlockM * 128)) + row * 8;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 f = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                slab[j ^ (row & 7)] = *reinterpret_cast<const uint4*>(&f);
+                            }
+                        }
+                        return;
                     }
                     uint4* xb = reinterpret_cast<uint4*>(s_xpose + ew * Cfg::kXposeBytesPerWarp);
                     const int nvalid = p.N - nc;                                   // < 32 in a ragged last chunk, <= 0 beyond N
@@ -613,6 +646,20 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         }
                         finish_chunk(v, n0 + c * 32);
                         if (stamp && ci == 0) stamps[15] = clock64();         // first chunk stored
+                    }
+                }
+                if (use_tma) {
+                    fence_proxy_async_smem();                        // my staged rows -> visible to the TMA
+                    epi_bar_sync<kEpiThreads>();                     // ... and everybody else's
+                    if (et == 0) {
+                        if (p.tma_store == 1) {
+                            for (int sl = 0; sl < BLOCK_N / 64; ++sl)
+                                if (n0 + sl * 64 < p.N) tma_store_2d(&tmap_c, ring + sl * (kBlockM * 128), n0 + sl * 64, m0);
+                        } else {
+                            for (int sl = 0; sl < BLOCK_N / 32; ++sl)
+                                if (n0 + sl * 32 < p.N) tma_store_2d(&tmap_c, ring + sl * (kBlockM * 128), n0 + sl * 32, m0);
+                        }
+                        tma_store_commit_and_wait_read();            // the ring is read before this CTA tears down
                     }
                 }
                 if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
@@ -788,7 +835,10 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
     fill_cfg<Cfg, LN>(cfg, attrs, grid, cluster, ep.pdl == 1 || ep.pdl == 5, st);
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, m_tiles, n_tiles);
+    GemmEpilogue e2 = ep;
+    const CUtensorMap* tc = static_cast<const CUtensorMap*>(ep.tmap_c_host);
+    if (tc == nullptr || LN || ep.split_k > 1) { e2.tma_store = 0; tc = &ta; }          // &ta: any valid map for the unused slot
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, *tc, e2, m_tiles, n_tiles);
 }
 
 }  // namespace pgemm

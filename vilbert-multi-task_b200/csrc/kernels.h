@@ -32,6 +32,9 @@ struct GemmEpilogue {
     int split_k;                  // plain kernel only: K is cut into split_k slices, slice s writes its fp32 partial sum to
     long long split_stride;       //   out_f32 + s * split_stride (bias added by slice 0); the row LayerNorm kernel sums them
     long long* timing;            // optional (profiling): 8 clock64 stamps per CTA, see gemm_persistent.cu; null in production
+    const void* tmap_c_host;      // host pointer to the CUtensorMap of the output (launchers copy it into a kernel parameter)
+    int tma_store;                // 0: register/LSU stores only; 1: 16-bit output, 2: fp32 output may leave through a TMA store
+                                  // (plain persistent kernel: the LAST tile of every CTA is staged in the idle operand ring)
     const void* prefetch;         // optional: the NEXT GEMM's weight matrix; the (otherwise idle) epilogue warps pull it into L2
     long long prefetch_bytes;     //   while this kernel's main loop runs -- a step touches 466 MB of weights, so without this
 };                                //   every GEMM starts on HBM misses (weights never survive in the 126 MB L2 until the next step)
