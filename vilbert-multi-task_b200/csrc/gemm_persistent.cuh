@@ -384,6 +384,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t my_rank = LN ? cluster_ctarank() : 0u;
 
     // ---------------------------------------------------------------- one-time setup
+    // The producer thread does not wait for the CTA-wide setup barrier: as soon as ITS barriers exist it puts the first ring
+    // pass of the first tile in flight -- activations and weights when the kernel has no programmatic dependency (pdl 0 / 2),
+    // only the weights (they do not depend on the previous kernel) when it was launched programmatically with pdl == 5; the
+    // activation tiles then follow after griddepcontrol.wait.
+    int early = 0;                 // k-blocks of the first tile already (partly) in flight     } producer thread only
+    bool early_a = false;          // ... including their activation tiles                       }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
@@ -398,6 +404,19 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             mbar_init(&ln_bar[a], LN ? cluster_size : 1u);                   // one arrival per CTA of the cluster
         }
         mbar_fence_init();
+        if (!LN && first_tile < total_tiles && p.pdl != 1) {
+            early_a = p.pdl != 5;
+            const int mn = first_tile / split_k, ks = first_tile % split_k;
+            const int m0 = (mn / num_n_tiles) * kBlockM, n0 = (mn % num_n_tiles) * BLOCK_N;
+            const int kb0 = ks * kbs, kb_end = min(num_kb, (ks + 1) * kbs);
+            early = min(kStages, kb_end - kb0);
+            for (int i = 0; i < early; ++i) {                  // fresh barriers: every slot is free
+                uint8_t* sa = ring + i * Cfg::kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
+                if (early_a) tma_load_2d(sa, &tmap_a, &full_bar[i], (kb0 + i) * kBlockK, m0);
+                tma_load_2d(sa + Cfg::kStageBytesA, &tmap_b, &full_bar[i], (kb0 + i) * kBlockK, n0);
+            }
+        }
     } else if (warp == 1) {
         tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
     } else if (LN && warp >= 2) {
@@ -414,32 +433,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (stamps && threadIdx.x == 0) stamps[1] = clock64();
 
-    // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The producer thread goes further:
-    // the weight tiles (W) do not depend on the previous kernel, so it puts the W loads of the first ring pass in flight
-    // BEFORE griddepcontrol.wait and only the activation tiles (A) after it.
-    const bool early_w = p.pdl == 5 && !LN;            // 5 = launched programmatically + early weight loads (kernels.h)
-    if (p.pdl && !(early_w && threadIdx.x == 0)) pdl_wait();
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; its outputs are visible after the
+    // wait.  (The producer thread of a pdl == 5 kernel waits inside its own branch, right before the first activation tile.)
+    if (p.pdl && !(p.pdl == 5 && !LN && threadIdx.x == 0)) pdl_wait();
 
     if (warp == 0) {
         // ============================================================ TMA producer
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            int early = 0;                                     // k-blocks of the first tile whose W tile is already in flight
-            if (early_w) {
-                if (first_tile < total_tiles) {
-                    const int mn = first_tile / split_k, ks = first_tile % split_k;
-                    const int n0 = (mn % num_n_tiles) * BLOCK_N;
-                    const int kb0 = ks * kbs, kb_end = min(num_kb, (ks + 1) * kbs);
-                    early = min(kStages, kb_end - kb0);
-                    for (int i = 0; i < early; ++i) {          // fresh barriers: every slot is free
-                        uint8_t* sb = ring + i * Cfg::kStageBytes + Cfg::kStageBytesA;
-                        mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
-                        tma_load_2d(sb, &tmap_b, &full_bar[i], (kb0 + i) * kBlockK, n0);
-                    }
-                }
-                pdl_wait();                                    // the previous kernel's outputs (A) are visible from here on
-            }
+            if (p.pdl == 5 && !LN) pdl_wait();
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
                 const int mn = LN ? tile : tile / split_k;
                 const int ks = LN ? 0 : tile % split_k;
@@ -449,9 +452,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 for (int kb = ks * kbs; kb < kb_end; ++kb) {
                     uint8_t* sa = ring + s * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kStageBytesA;
-                    if (early > 0) {                           // first ring pass of the first tile: W is already on its way
+                    if (early > 0) {                           // first ring pass of the first tile: already (partly) in flight
                         --early;
-                        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+                        if (!early_a) tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
                     } else {
                         mbar_wait(&empty_bar[s], phase ^ 1u);
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
