@@ -176,6 +176,100 @@ __device__ __forceinline__ void attend_tile(const uint16_t* Qs, const uint16_t* 
     }
 }
 
+// Short key sequences (nk <= 64: every default ViLBERT shape) need no online softmax: one warp computes S = Q K^T and the
+// probabilities ONCE for its 16 query rows and then walks the head's 64-column output slices (the general routine above would
+// recompute S and the softmax per slice).  Same arithmetic, same order of operations per output element.
+template <int D, bool F16>
+__device__ __forceinline__ void attend_tile_short(const uint16_t* Qs, const uint16_t* Ks, const uint16_t* Vs, int r0, int nq,
+                                                  int nk, const float* mask_l2, float scale_l2, uint16_t* out, int ld_out,
+                                                  int lane) {
+    constexpr int kStride = AttnTile<D>::kStride;
+    constexpr int kKSteps = D / 16;
+    const int g = lane >> 2, tq = lane & 3;
+    const int nkeys = pad16(nk);                                  // <= 64, multiple of 16
+    float s[kKeyBlock / 8][4];
+    {
+        uint32_t qa[kKSteps][4];
+#pragma unroll
+        for (int ks = 0; ks < kKSteps; ++ks)
+            ldsm_x4(qa[ks], Qs + (r0 + (lane & 15)) * kStride + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int nt = 0; nt < kKeyBlock / 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+            if (nt * 8 < nkeys) {
+#pragma unroll
+                for (int ks2 = 0; ks2 < kKSteps / 2; ++ks2) {
+                    uint32_t kf[4];
+                    ldsm_x4(kf, Ks + (nt * 8 + (lane & 7)) * kStride + ks2 * 32 + (lane >> 3) * 8);
+                    mma16816<F16>(s[nt], qa[2 * ks2], kf[0], kf[1]);
+                    mma16816<F16>(s[nt], qa[2 * ks2 + 1], kf[2], kf[3]);
+                }
+            }
+        }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < kKeyBlock / 8; ++nt) {
+        if (nt * 8 < nkeys) {
+            const int j = nt * 8 + tq * 2;
+            const float ma = j < nk ? mask_l2[j] : -INFINITY;
+            const float mb = j + 1 < nk ? mask_l2[j + 1] : -INFINITY;
+            s[nt][0] = fmaf(s[nt][0], scale_l2, ma); s[nt][1] = fmaf(s[nt][1], scale_l2, mb);
+            s[nt][2] = fmaf(s[nt][2], scale_l2, ma); s[nt][3] = fmaf(s[nt][3], scale_l2, mb);
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.0f, l1 = 0.0f;
+    uint32_t pa[kKeyBlock / 16][4];                               // probabilities as A fragments (16 keys each)
+#pragma unroll
+    for (int nt = 0; nt < kKeyBlock / 8; ++nt) {
+        if (nt * 8 < nkeys) {
+            s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
+            s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < kKeyBlock / 16; ++kk) {
+        pa[kk][0] = pack16x2<F16>(s[2 * kk][0], s[2 * kk][1]);
+        pa[kk][1] = pack16x2<F16>(s[2 * kk][2], s[2 * kk][3]);
+        pa[kk][2] = pack16x2<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[kk][3] = pack16x2<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+#pragma unroll
+    for (int oc0 = 0; oc0 < D; oc0 += 64) {                       // 64 output columns at a time: 32 accumulator registers
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < kKeyBlock / 16; ++kk) {
+            if (kk * 16 < nkeys) {
+#pragma unroll
+                for (int nt2 = 0; nt2 < 4; ++nt2) {
+                    uint32_t vf[4];
+                    ldsm_x4_trans(vf, Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kStride + oc0 + nt2 * 16 + (lane >> 4) * 8);
+                    mma16816<F16>(o[2 * nt2], pa[kk], vf[0], vf[1]);
+                    mma16816<F16>(o[2 * nt2 + 1], pa[kk], vf[2], vf[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int col = oc0 + nt * 8 + tq * 2;
+            if (row0 < nq) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row0) * ld_out + col) = pack16x2<F16>(o[nt][0] * i0, o[nt][1] * i0);
+            if (row1 < nq) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row1) * ld_out + col) = pack16x2<F16>(o[nt][2] * i1, o[nt][3] * i1);
+        }
+    }
+}
+
 template <int D, bool F16>
 __global__ void __launch_bounds__(256, 2)     // <= 128 registers: 5 CTAs of 3-4 warps per SM -> one wave at batch 64
 self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, const float* __restrict__ key_mask_add,
@@ -202,6 +296,11 @@ self_attention_kernel(const uint16_t* __restrict__ qkv, int ld_qkv, int hidden, 
     if (pdl) pdl_launch_dependents();       // tiles are staged: the next kernel's prologue may overlap the math
     uint16_t* outp = ctx + static_cast<size_t>(b) * L * ld_ctx + h * D;
     constexpr int kSplit = D / 64, kOW = D / kSplit;             // work item = (16-row tile, 64-column slice of the head)
+    if (L <= kKeyBlock) {                                        // one key block: S and the softmax once per row tile
+        for (int t = warp; t * 16 < L; t += nwarps)
+            attend_tile_short<D, F16>(Qs, Ks, Vs, t * 16, L, L, mask_s, scale_l2, outp, ld_ctx, lane);
+        return;
+    }
     for (int w = warp; (w / kSplit) * 16 < L; w += nwarps)
         attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, L, L, mask_s, scale_l2, outp, ld_ctx, lane, (w % kSplit) * kOW);
 }
@@ -241,8 +340,13 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
     __syncthreads();
     uint16_t* out_t = ctx_txt + static_cast<size_t>(b) * T * ld_ctx_txt + h * D;
     constexpr int kSplit = D / 64, kOW = D / kSplit;
-    for (int w = warp; (w / kSplit) * 16 < T; w += nwarps)
-        attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane, (w % kSplit) * kOW);
+    if (V <= kKeyBlock) {
+        for (int t = warp; t * 16 < T; t += nwarps)
+            attend_tile_short<D, F16>(Qs, Ks, Vs, t * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane);
+    } else {
+        for (int w = warp; (w / kSplit) * 16 < T; w += nwarps)
+            attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, T, V, mask_img, scale_l2, out_t, ld_ctx_txt, lane, (w % kSplit) * kOW);
+    }
     __syncthreads();                                             // everyone is done reading phase-1 tiles
     load_tile<D>(Qs, bi, V, Vp, ld_img);                         // Q1
     load_tile<D>(Ks, bt + hidden, T, Tp, ld_txt);                // K2
@@ -251,8 +355,13 @@ co_attention_kernel(const uint16_t* __restrict__ qkv_img, int ld_img, const uint
     __syncthreads();
     if (pdl) pdl_launch_dependents();
     uint16_t* out_v = ctx_img + static_cast<size_t>(b) * V * ld_ctx_img + h * D;
-    for (int w = warp; (w / kSplit) * 16 < V; w += nwarps)
-        attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane, (w % kSplit) * kOW);
+    if (T <= kKeyBlock) {
+        for (int t = warp; t * 16 < V; t += nwarps)
+            attend_tile_short<D, F16>(Qs, Ks, Vs, t * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane);
+    } else {
+        for (int w = warp; (w / kSplit) * 16 < V; w += nwarps)
+            attend_tile<D, kOW, F16>(Qs, Ks, Vs, (w / kSplit) * 16, V, T, mask_txt, scale_l2, out_v, ld_ctx_img, lane, (w % kSplit) * kOW);
+    }
 }
 
 template <int D, bool F16>

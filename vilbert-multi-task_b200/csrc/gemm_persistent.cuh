@@ -557,8 +557,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     bias_act32<ACT>(v, bias_t + (nc - n0));
                     if (p.mul != nullptr && m_ok) {
                         const float* mp = p.mul + static_cast<size_t>(m) * p.ld_mul + nc;
+                        if ((p.ld_mul & 3) == 0 && nc + 32 <= p.N) {          // 8 x 16-byte loads instead of 32 scalar ones
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 f = reinterpret_cast<const float4*>(mp)[j];
+                                v[4 * j] *= f.x; v[4 * j + 1] *= f.y; v[4 * j + 2] *= f.z; v[4 * j + 3] *= f.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (nc + j < p.N) v[j] *= mp[j];
+                        }
                     }
                     if (use_tma) {
                         // last tile of this CTA: the operand ring is idle -> stage the tile there in the TMA's SWIZZLE_128B
