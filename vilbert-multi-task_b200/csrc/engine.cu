@@ -392,6 +392,7 @@ struct vb200_engine {
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
     bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
     bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
+    bool split_k_fixed = false;     // VB200_SPLITK=2
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
     // batches in flight, per step: off 1.597-1.604 ms | full 1.567 | "mediumplus" (everything except edges across a fork / join)
@@ -702,6 +703,8 @@ struct vb200_engine {
                 split_k = static_cast<int>(std::min<long long>(kMaxSplitK, std::max<long long>(1, 296 / tiles)));
                 while (split_k > 1 && num_kb / split_k < 6) --split_k;
             }
+            // VB200_SPLITK=2: a split that depends on K only (K >= 2048 -> two halves), so results stay independent of the batch
+            if (split_k_fixed && !gemm_v1 && !op.pair && act == vb::kActNone && num_kb >= 32 && tiles <= 2 * 148) split_k = 2;
             e.split_k = split_k;
             e.split_stride = static_cast<long long>(a_rows) * W.N;
         } else {
@@ -1165,7 +1168,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         if (const char* v = getenv("VB200_GEMM")) eng->gemm_v1 = (strcmp(v, "v1") == 0);
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
-        if (const char* v = getenv("VB200_SPLITK")) eng->split_k_enabled = (strcmp(v, "1") == 0);
+        if (const char* v = getenv("VB200_SPLITK")) { eng->split_k_enabled = (strcmp(v, "1") == 0); eng->split_k_fixed = (strcmp(v, "2") == 0); }
         eng->pdl_light = eng->pdl_medium = false;
         if (pdl_req == 0) eng->opt.use_pdl = 1;               // default: full
         if (const char* v = getenv("VB200_PDL")) {
