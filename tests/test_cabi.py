@@ -182,3 +182,19 @@ def test_product_path_never_imports_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_c_host_example_builds_and_runs(tmp_path):
+    """examples/host_min.c: a plain C program binds the library with nothing but include/vilbert_b200.h (dlopen), checks the ABI
+    version and gets status + message for a bad config and an incomplete checkpoint -- all before any device is touched."""
+    import shutil
+    import subprocess
+    from vilbert_b200 import _lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "host_min"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "host_min.c"), "-o", str(exe), "-ldl"], check=True)
+    r = subprocess.run([str(exe), L.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bad config       -> -2" in r.stdout and "empty checkpoint -> -3" in r.stdout and r.stdout.strip().endswith("ok")
