@@ -27,3 +27,16 @@ def test_reference_arm_json_line():
     e2e = j["e2e"]
     assert e2e["value"] == j["value"] and e2e["unit"] == j["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    """No CUDA device: the product arm must refuse (non-zero exit, no JSON line) instead of falling back to anything."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert "no CPU fallback" in (r.stderr + r.stdout)
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
