@@ -92,6 +92,29 @@ def test_text_layer_matches_huggingface_bert(full_oracle):
     assert torch.allclose(out, ref, atol=2e-5), float((out - ref).abs().max())
 
 
+def test_text_embeddings_match_huggingface_bert(full_oracle):
+    """Independent pin of the BertEmbeddings restatement: word + position + token-type gather-sum and LayerNorm(eps 1e-12) through
+    transformers' BertEmbeddings on the same weights; the task-token row ViLBERT inserts at index 1 is the only difference."""
+    pytest.importorskip("transformers")
+    from transformers.models.bert.modeling_bert import BertConfig as HFConfig, BertEmbeddings as HFEmb
+    hf = HFEmb(HFConfig(vocab_size=30522, hidden_size=768, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                        hidden_dropout_prob=0.0, pad_token_id=0)).eval()
+    ours = full_oracle.bert.embeddings
+    sd = {k: v for k, v in ours.state_dict().items() if not k.startswith("task_embeddings")}
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in m or "token_type_ids" in m for m in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, 30522, (3, 30), generator=g)
+    seg = torch.randint(0, 2, (3, 30), generator=g)
+    with torch.no_grad():
+        ref = hf(input_ids=ids, token_type_ids=seg)
+        out = ours(ids, seg, torch.full((3, 1), 7))
+    assert out.shape == (3, 31, 768)
+    assert torch.allclose(torch.cat([out[:, :1], out[:, 2:]], dim=1), ref, atol=1e-5)
+    task_row = ours.LayerNorm(ours.task_embeddings(torch.full((3, 1), 7)))
+    assert torch.allclose(out[:, 1:2], task_row, atol=1e-6)             # no position / type embedding on the task token
+
+
 def test_gelu_and_layernorm_definitions():
     x = torch.linspace(-4, 4, 101)
     assert torch.allclose(R.gelu(x), torch.nn.functional.gelu(x), atol=1e-6)          # erf form
