@@ -14,8 +14,9 @@ for this path (demo/tests.py:1-3 is an empty stub).  This file therefore restate
 algorithm (arXiv:1908.02265 section 3, arXiv:1912.02315) constrained by every in-tree call site;
 there is nothing in /root/reference to pin it against numerically  ==>  "parity unpinned".
 The one number the tree does pin -- "270 million" parameters (README.md:4) -- is checked by
-``count_parameters`` (268.0 M unique parameters, the tied LM decoder counted once).  The text ``BertLayer`` restatement is additionally cross-checked
-against the independent implementation in HuggingFace ``transformers`` (tests/test_oracle.py).
+``count_parameters`` (268.0 M unique parameters, the tied LM decoder counted once).  Three pieces are additionally
+cross-checked against independent implementations (tests/test_oracle.py): the text ``BertLayer`` and ``BertEmbeddings`` against
+HuggingFace ``transformers``, both directions of the co-attention against ``torch.nn.MultiheadAttention``.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
 ``bench.py`` may import this module; the product path (``vilbert_b200``) never does.
