@@ -32,8 +32,15 @@ constexpr int kUmmaK = 16;
 
 // EPI8: eight epilogue warps (two column groups per TMEM lane quarter) -- every instantiation uses it now (KCfg); with four,
 // each SM sub-partition ran ONE epilogue warp and every dependent instruction paid its full latency.
-template <int BLOCK_N, bool LN, bool EPI8 = LN, bool DEEP = false>
+// MODE 0: default.  MODE 1 ("DEEP"): one CTA per SM, deep ring, two MMA issuers (see below).  MODE 2 ("WIDE2", BLOCK_N = 256 only):
+// 128x256 tiles at TWO CTAs per SM -- a 256-wide MMA takes 128 cycles, so the one-issuer limit (134 cycles per MMA) does not
+// bite, and two CTAs keep both the tensor pipe and the ~98 B/clk operand ingest busy; paid for with a 2-stage 48 KB ring, a
+// single-buffered 256-column accumulator and the bias read through L1 instead of shared memory (the budget is 96 bytes short).
+template <int BLOCK_N, bool LN, bool EPI8 = LN, int MODE = 0>
 struct PCfg {
+    static constexpr bool DEEP = MODE == 1;
+    static constexpr bool WIDE2 = MODE == 2;
+    static_assert(!WIDE2 || (BLOCK_N == 256 && !LN), "WIDE2 is the 256-wide plain tile");
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
@@ -50,14 +57,14 @@ struct PCfg {
     // DEEP: one CTA per SM with the whole ring to itself.  A lone CTA with the 3-stage ring is latency-bound at ~540 cycles per
     // k-block (3 x 32 KB per ~1600-cycle L2 round trip, measured); GEMMs with no more tiles than SMs (N = 768 / 1024 at batch
     // 64, every M = 64 head) therefore take the deep ring and 8 epilogue warps (their one epilogue per CTA is fully exposed).
-    static constexpr int kMinBlocks = (LN || BLOCK_N >= 192 || DEEP) ? 1 : 2;
+    static constexpr int kMinBlocks = WIDE2 ? 2 : ((LN || BLOCK_N >= 192 || DEEP) ? 1 : 2);
     // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
     // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
     //   plain: 32 rows x 64 bytes, XOR-swizzled (store16_sw / store_f32_sw);  LN: 32 rows x 33 fp32
     static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 2048;      // plain: 32 rows x 64 B, swizzled (store16_sw)
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
-    static constexpr int kStages = kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit);
+    static constexpr int kStages = WIDE2 ? 2 : (kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit));
     // Accumulator layout in TMEM.  Normal: two buffers of BLOCK_N columns (epilogue of tile i overlaps the MMAs of tile i+1).
     // DEEP: ONE buffer of kChains x BLOCK_N columns.  Measured: one thread issues at most one tcgen05.mma per ~134 cycles
     // whatever the instruction's N (536 cycles per k-block for BLOCK_N = 64, 128 and 256 alike, with 3 or 6 ring stages, with
@@ -66,7 +73,7 @@ struct PCfg {
     // warp the odd ones, each into its OWN accumulator chain so the fp32 summation order stays fixed (the epilogue adds the
     // two chains) -- results do not depend on how the two warps interleave.
     static constexpr int kChains = kMmaWarps;
-    static constexpr int kAccBufs = DEEP ? 1 : 2;
+    static constexpr int kAccBufs = (DEEP || WIDE2) ? 1 : 2;
     static constexpr int kAccCols = kChains * kAccBufs * BLOCK_N;
     static_assert(kAccCols <= 512, "TMEM has 512 columns");
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
@@ -77,7 +84,8 @@ struct PCfg {
     // LN-only pieces (gamma, beta, cluster partials) cost nothing in the plain kernel, whose budget is 233472 / 2 - 1024
     static constexpr int kLnAux = LN ? 2 * BLOCK_N * 4 + 4 * kBlockM * 8 : 0;
     // plain: ONE bias slice (the tile-end barrier of the epilogue warps protects it); LN keeps bias | gamma | beta resident
-    static constexpr int kBiasFloats = LN ? 2 * BLOCK_N : BLOCK_N;
+    static constexpr bool kBiasInSmem = !WIDE2;
+    static constexpr int kBiasFloats = LN ? 2 * BLOCK_N : (kBiasInSmem ? BLOCK_N : 0);
     static constexpr int kSmemAux = kBiasFloats * 4 + kLnAux + kNumBars * 8 + 16 + kXposeBytes;
     // no alignment slack: the dynamic shared-memory window starts 1024-aligned (checked at kernel entry).  An SM has 233472
     // bytes and every CTA costs its dynamic size + 1024 reserved.
@@ -321,17 +329,17 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
     __syncwarp();
 }
 
-template <int BLOCK_N, bool LN, int ACT, bool DEEP = false>
-struct KCfg { using type = PCfg<BLOCK_N, LN, true, DEEP>; };   // 8 epilogue warps everywhere: with 4, each SM sub-partition
+template <int BLOCK_N, bool LN, int ACT, int MODE = 0>
+struct KCfg { using type = PCfg<BLOCK_N, LN, true, MODE>; };   // 8 epilogue warps everywhere: with 4, each SM sub-partition
                                                                  // runs ONE epilogue warp -- every dependent instruction pays
                                                                  // its full latency (~4 k cycles per 128x128 tile, measured)
 
-template <int BLOCK_N, bool LN, int ACT, bool F16, bool DEEP = false>
-__global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT, DEEP>::type::kThreads, KCfg<BLOCK_N, LN, ACT, DEEP>::type::kMinBlocks)
+template <int BLOCK_N, bool LN, int ACT, bool F16, int MODE = 0>
+__global__ void __launch_bounds__(KCfg<BLOCK_N, LN, ACT, MODE>::type::kThreads, KCfg<BLOCK_N, LN, ACT, MODE>::type::kMinBlocks)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_c, const GemmEpilogue p, const int num_m_tiles,
                        const int num_n_tiles) {
-    using Cfg = typename KCfg<BLOCK_N, LN, ACT, DEEP>::type;
+    using Cfg = typename KCfg<BLOCK_N, LN, ACT, MODE>::type;
     constexpr int kStages = Cfg::kStages;
     constexpr int kNC = Cfg::kNumChunks;
     constexpr int kEpiThreads = Cfg::kEpiThreads;
@@ -539,18 +547,24 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
             if constexpr (!LN) {
                 // ------------------------------------------------ plain epilogue: 4 warps, chunk-pipelined
-                float* bias_t = s_bias;
-                // per-tile bias slice; the barrier below orders it before the reads, the one at the end of the tile orders
-                // the reads before the next tile's writes
-                for (int i = et; i < BLOCK_N; i += kEpiThreads) bias_t[i] = (p.bias && ks == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
-                epi_bar_sync<kEpiThreads>();
+                const float* bias_t = s_bias;
+                if constexpr (Cfg::kBiasInSmem) {
+                    // per-tile bias slice; the barrier below orders it before the reads, the one at the end of the tile orders
+                    // the reads before the next tile's writes
+                    for (int i = et; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (p.bias && ks == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
+                    epi_bar_sync<kEpiThreads>();
+                } else {
+                    bias_t = p.bias + n0;                  // WIDE2: straight from global / L1 (host guarantees bias != null, N % 256 == 0)
+                }
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (stamp) stamps[4] = clock64();
                 float* const out_f32 = p.out_f32 ? p.out_f32 + static_cast<long long>(ks) * p.split_stride : nullptr;   // split-K slice
                 // TMA-store path (CTA-uniform): this is the CTA's last tile, so no operand load is or will be in flight and
                 // every MMA that read the ring has completed (tmem_full above)
+                constexpr bool kF32SlabsFit = (BLOCK_N / 32) * (kBlockM * 128) <= kStages * Cfg::kStageBytes;
                 const bool use_tma = p.tma_store != 0 && st_fast && tile + tile_stride >= total_tiles &&
+                                     (p.tma_store == 1 || kF32SlabsFit) &&
                                      (p.tma_store == 1 ? (p.out_bf16 != nullptr && p.out_f32 == nullptr)
                                                        : (p.out_f32 != nullptr && p.out_bf16 == nullptr));
                 auto finish_chunk = [&](float (&v)[32], int nc) {
@@ -674,7 +688,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                 }
                 if (stamp) { stamps[5] = clock64(); stamps[7] = clock64(); }
-                if (tile + tile_stride < total_tiles) epi_bar_sync<kEpiThreads>();     // bias slice free for the next tile
+                if (Cfg::kBiasInSmem && tile + tile_stride < total_tiles) epi_bar_sync<kEpiThreads>();   // bias slice free for the next tile
             } else {
                 // ------------------------------------------------ LayerNorm epilogue: 8 warps, row slice in registers
                 constexpr int kCPT = Cfg::kCPT;
@@ -826,10 +840,10 @@ void fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, dim3 grid, in
 }
 
 // resident: LN only -- how many clusters of this size can be co-resident (grid.y is capped to it)
-template <int BLOCK_N, bool LN, int ACT, bool F16, bool DEEP = false>
+template <int BLOCK_N, bool LN, int ACT, bool F16, int MODE = 0>
 cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int resident, cudaStream_t st) {
-    using Cfg = typename KCfg<BLOCK_N, LN, ACT, DEEP>::type;
-    auto kern = gemm_persistent_kernel<BLOCK_N, LN, ACT, F16, DEEP>;
+    using Cfg = typename KCfg<BLOCK_N, LN, ACT, MODE>::type;
+    auto kern = gemm_persistent_kernel<BLOCK_N, LN, ACT, F16, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     const int n_tiles = (ep.N + BLOCK_N - 1) / BLOCK_N;

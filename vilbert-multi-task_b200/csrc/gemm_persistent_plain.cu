@@ -31,6 +31,17 @@ static cudaError_t dispatch_plain(const CUtensorMap& ta, const CUtensorMap& tb, 
         if (deep_mode != 0 && tiles <= num_sms() && (deep_mode == 1 || ep.M <= kBlockM))
             return dispatch_deep<BN>(ta, tb, ep, st);
     }
+    if constexpr (BN == 256) {
+        // 128x256 tiles at two CTAs per SM (PCfg MODE 2); experiment: VB200_WIDE2=1 (with VB200_BN=256 to select the tile width)
+        static const bool wide2 = getenv("VB200_WIDE2") != nullptr && atoi(getenv("VB200_WIDE2")) != 0;
+        if (wide2 && ep.N % 256 == 0 && ep.bias != nullptr && ep.split_k <= 1) {
+            switch (ep.act) {
+                case kActNone: return f16 ? launch_p<256, false, kActNone, true, 2>(ta, tb, ep, 0, st) : launch_p<256, false, kActNone, false, 2>(ta, tb, ep, 0, st);
+                case kActGelu: return f16 ? launch_p<256, false, kActGelu, true, 2>(ta, tb, ep, 0, st) : launch_p<256, false, kActGelu, false, 2>(ta, tb, ep, 0, st);
+                case kActRelu: return f16 ? launch_p<256, false, kActRelu, true, 2>(ta, tb, ep, 0, st) : launch_p<256, false, kActRelu, false, 2>(ta, tb, ep, 0, st);
+            }
+        }
+    }
     switch (ep.act) {
         case kActNone: return f16 ? launch_p<BN, false, kActNone, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActNone, false>(ta, tb, ep, 0, st);
         case kActGelu: return f16 ? launch_p<BN, false, kActGelu, true>(ta, tb, ep, 0, st) : launch_p<BN, false, kActGelu, false>(ta, tb, ep, 0, st);
