@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VB200_ABI_VERSION 1
+#define VB200_ABI_VERSION 2
 
 typedef struct vb200_engine* vb200_handle;
 
@@ -66,7 +66,11 @@ enum {
     VB200_OUT_LINGUISIC_PREDICTION = 1 << 7,   /* [B, T, vocab]    pre-training head, unused by the worker */
     VB200_OUT_LINGUISIC_LOGIT = 1 << 8,        /* [B, T, 1]        never read by the worker */
     VB200_OUT_TASK_HEADS = 0x15F,              /* the seven task heads (everything but the two pre-training heads) */
-    VB200_OUT_ALL = 0x1FF
+    VB200_OUT_ALL = 0x1FF,
+    VB200_OUT_ATTENTION = 1 << 9               /* element 9 of the tuple, attn_data_list: the attention probabilities of all 24 layers
+                                                  (worker.py:287-288; the reference returns them because config.visualization is set,
+                                                  worker.py:522, and never reads them).  Off unless requested: see
+                                                  vb200_attention_layout and vb200_outputs.attention_probs. */
 };
 
 /* Inputs of one forward, in the dtypes the worker builds them (worker.py:416-419, 452-455).
@@ -100,6 +104,9 @@ typedef struct {
     float* sequence_output_t;      /* optional debug tap: final text stream  [B, T, hidden]   (fp32) */
     float* sequence_output_v;      /* optional debug tap: final image stream [B, V, v_hidden] (fp32) */
     float* pooled_output;          /* optional debug tap: pooled_t * pooled_v [B, bi_hidden] */
+    float* attention_probs;        /* VB200_OUT_ATTENTION: one flat fp32 buffer holding every layer's softmax probabilities
+                                      [B, heads, Lq, Lk] back to back in execution order (vb200_attention_layout gives the
+                                      offsets); NULL skips the copy */
 } vb200_outputs;
 
 /* Engine options (all optional; zero-initialise for defaults).  Flags are tri-state: 0 default, 1 on, -1 off. */
@@ -117,19 +124,32 @@ typedef struct {
                                       kernel; 1: cluster-LayerNorm GEMM epilogue (N tiles of a row-panel form a thread-block
                                       cluster and exchange (mean, M2) through distributed shared memory).  Both are
                                       parity-tested; the split form measured faster on B200 at every batch tried. */
+    int32_t split_fp32;            /* 1: fp32-parity mode ("fp32x").  Every GEMM operand travels as TWO fp16 numbers (hi = fp16(x),
+                                      lo = fp16(x - hi), 22 significand bits); operand buffers hold hi | lo | hi (weights hi | hi |
+                                      lo) per 64 columns, so an ordinary tcgen05 GEMM over K' = 3K adds hi.hi + lo.hi + hi.lo in its
+                                      fp32 accumulator; attention runs in fp32 on CUDA cores; GELU uses the 1.5e-7 erf.  3x the
+                                      tensor work of the default mode -- for logit parity with the reference's fp32 forward
+                                      (<= 1e-3 per logit, BASELINE.json north_star), not for throughput.  Implies act_fp16. */
+    int32_t max_plans;             /* plan-cache bound: plans (workspace + CUDA graph per (batch, tokens, regions, select, slot))
+                                      beyond this are evicted least-recently-used; 0 -> 24 */
 } vb200_options;
 
 int vb200_abi_version(void);
 
 /* from_pretrained + cuda(device): parse the BertConfig JSON, audit the state_dict against the upstream key list,
- * repack weights to device (bf16 GEMM operands, fp32 LayerNorm/bias/embedding tables). */
+ * repack weights to device (16-bit GEMM operands in the format vb200_options::act_fp16 selects -- fp16 by default, bf16, or the
+ * fp16 hi/lo pairs of split_fp32 -- and fp32 LayerNorm / bias / embedding tables). */
 int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor* tensors, const vb200_options* opt,
                  vb200_handle* out);
 int vb200_destroy(vb200_handle h);
 const char* vb200_last_error(vb200_handle h);
 
 /* Device-pointer forward (what worker.py:286-289 does): all vb200_inputs / vb200_outputs pointers are device
- * memory on the engine's device; enqueued on `cuda_stream` (a cudaStream_t passed as void*). */
+ * memory on the engine's device; enqueued on `cuda_stream` (a cudaStream_t passed as void*).
+ * Synchronisation: a call whose (batch, n_tokens, n_regions, select, slot) plan already exists only enqueues work and returns.
+ * The FIRST call of a shape builds its plan: cudaMalloc of the workspace, one eager validation pass with a stream
+ * synchronisation, and the CUDA-graph capture -- it blocks the host for some milliseconds and may synchronise the device (also
+ * when the plan cache evicts an old plan, vb200_options::max_plans).  Warm a server's shapes up before taking traffic. */
 int vb200_forward(vb200_handle h, const vb200_inputs* in, const vb200_outputs* out, uint32_t select, void* cuda_stream);
 
 /* Same with an explicit workspace slot (0..15): forwards on DIFFERENT slots may run concurrently on different streams (each
@@ -160,20 +180,83 @@ int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
 int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select, int32_t iters,
                       int32_t max_ops, int32_t* n_ops, int32_t* kinds, double* ms, double* flops, int32_t* dims);
 
+/* Layout of vb200_outputs.attention_probs for a shape: entry i is a [batch, dims[4i], dims[4i+1], dims[4i+2]] fp32 tensor
+ * (heads, query length, key length) at float offset offsets[i]; dims[4i+3] is the layer kind: 0 text layer, 1 image layer,
+ * 2 connection layer, text queries over image keys, 3 connection layer, image queries over text keys (kinds 2 and 3 of one layer
+ * are adjacent: the reference's per-layer tuple).  *n_entries receives the entry count (30 for the 12/6/6 configuration: 24
+ * layers, two tensors per connection layer), total_floats the buffer size.  Arrays may be NULL to query the count only. */
+int vb200_attention_layout(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, int32_t max_entries,
+                           int32_t* n_entries, int32_t* dims, int64_t* offsets, int64_t* total_floats);
+
+/* custom_prediction()'s tensor construction fused into the forward (worker.py:422-455): instead of features [B, V, F] /
+ * spatials [B, V, 5] / image_mask the caller passes what the detector produced -- box features, pixel boxes, image sizes -- and one
+ * kernel writes the image-embedding GEMM's 16-bit operand rows directly: global mean row first, 5-d normalised locations
+ * ([0,0,1,1,1] for the global row), masks.  n_regions of the forward is n_boxes + 1. */
+typedef struct {
+    int32_t batch;                 /* images (= rows of the forward) */
+    int32_t n_tokens;              /* Tin */
+    int32_t n_boxes;               /* detector boxes per image (rows of box_features per image); n_regions = n_boxes + 1 */
+    const int64_t* question;       /* [B, Tin]   (text already repeated per image for pair / retrieval tasks, worker.py:266-284) */
+    const int64_t* segment_ids;    /* [B, Tin] */
+    const int64_t* input_mask;     /* [B, Tin] */
+    const int64_t* task_tokens;    /* [B, 1] */
+    const float* box_features;     /* [B, n_boxes, v_feature_size] fp32, as the detector returns them (worker.py:213) */
+    const float* boxes;            /* [B, n_boxes, 4] pixel x1, y1, x2, y2 (infos[i]['bbox'], worker.py:434) */
+    const float* image_wh;         /* [B, 2] image_width, image_height */
+    const int32_t* num_boxes;      /* [B] valid boxes per image or NULL (= n_boxes); padded boxes are zeroed, masked and left out
+                                      of the mean */
+    float* spatials_out;           /* optional [B, n_boxes + 1, 5]: the spatials tensor the reference would have built (the
+                                      grounding decode reads spatials[0], worker.py:379) */
+} vb200_region_inputs;
+int vb200_forward_regions(vb200_handle h, const vb200_region_inputs* in, const vb200_outputs* out, uint32_t select, int32_t slot,
+                          void* cuda_stream);
+
+/* ---- Caption-image retrieval with reuse (reference semantics worker.py:278-284, 359).  Everything ahead of
+ * the first connection layer depends on the caption alone or on the image alone: encode each caption / image ONCE, then score
+ * pairs from the cached states.  Same kernels on the same rows as the full forward: scores are bit-identical to vb200_forward.
+ * State buffers are caller-allocated device memory: fp32 [n, L, hidden], 16-bit [n, L, hidden * operand_width_factor] (2 bytes per
+ * element; vb200_model_dim "operand_width_factor" is 1, or 3 in split_fp32 mode) and the additive mask fp32 [n, L], with
+ * L = n_tokens + 1 (task token) for text and L = n_regions for images. */
+int vb200_encode_text(vb200_handle h, int32_t n, int32_t n_tokens, const int64_t* question, const int64_t* segment_ids,
+                      const int64_t* input_mask, const int64_t* task_tokens, float* state_f32, void* state_16, float* state_mask,
+                      void* cuda_stream);
+int vb200_encode_image(vb200_handle h, int32_t n, int32_t n_regions, const float* features, const float* spatials,
+                       const uint8_t* image_mask, float* state_f32, void* state_16, float* state_mask, void* cuda_stream);
+/* Pair b = (caption text_index[b], image image_index[b]); index arrays are device int32. */
+int vb200_forward_cached(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, const int32_t* text_index,
+                         int32_t n_text, const float* text_f32, const void* text_16, const float* text_mask,
+                         const int32_t* image_index, int32_t n_image, const float* image_f32, const void* image_16,
+                         const float* image_mask, const vb200_outputs* out, uint32_t select, int32_t slot, void* cuda_stream);
+
 /* ---- Kernel-level entry points (device pointers), used by the parity tests and the roofline bench.  ---- */
 /* y = epilogue(x[M,K] (16-bit) . w[N,K]^T (16-bit)); act: 0 none, 1 GELU(erf), 2 ReLU; LayerNorm applied when gamma != NULL.
  * act_fp16 != 0: x, w and the 16-bit output y are fp16, else bf16 (parameter names keep the historical _bf16 suffix).
- * variant 0: persistent kernel (gemm_persistent.cu, what the engine uses); 1: one-tile-per-CTA kernel (gemm_tcgen05.cu).
+ * act 3 = GELU with the 1.5e-7 erf (fp32-parity mode).  variant 0: persistent kernel (gemm_persistent.cuh, what the engine
+ * uses); 2: CTA-pair kernel (gemm_pair.cu, cta_group::2).
  * timing: NULL, or a device buffer of 8 int64 per CTA that receives clock64() phase stamps (profiling aid, variant 0). */
 int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t ld_w, const float* bias,
                  const float* residual, int64_t ld_res, const float* gamma, const float* beta, float eps, int32_t act,
                  void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
                  int32_t block_n, int32_t use_pdl, int32_t act_fp16, int32_t variant, long long* timing, void* cuda_stream);
+/* The same GEMM on fp32-parity-mode operands (fp16 only): x16 holds hi | lo | hi and w16 hi | hi | lo per 64 logical columns, K3 is
+ * the PHYSICAL contraction length (3x the logical one), y16 (optional) is written in the activation split layout (stride ld_y16 of
+ * the 3x wider buffer), y_f32 (optional) as usual. */
+int vb200_linear_split(const void* x16, int64_t ld_x, const void* w16, int64_t ld_w, const float* bias, int32_t act, void* y16,
+                       int64_t ld_y16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K3, void* cuda_stream);
 /* ctx = softmax(Q K^T / sqrt(d) + mask) V, qkv rows = [Q | K | V] (bf16), mask_add fp32 [B, L]. */
 /* out = LayerNorm(y + residual) * gamma + beta over rows of N (N % 128 == 0, N <= 2048); fp32 and/or 16-bit outputs. */
 int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
                     float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
                     int32_t act_fp16, void* cuda_stream);
+/* split16 != 0: out_16 is the fp16 hi | lo | hi operand (stride ld_16 of the 3x wider buffer). */
+int vb200_layernorm_split(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
+                          float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N, void* cuda_stream);
+/* fp32 CUDA-core attention (attention_f32.cu): q / k / v point at head 0 of sample 0 (row strides ld_q, ld_kv; the three may alias
+ * one QKV buffer), in_kind 0 fp32 / 1 fp16 / 2 bf16; ctx_mode 0 no context / 1 fp16 / 2 bf16 / 3 fp16 hi | lo | hi;
+ * probs optional [B, heads, Lq, Lk]. */
+int vb200_attention_f32(const void* q, int64_t ld_q, const void* k, const void* v, int64_t ld_kv, int32_t in_kind,
+                        const float* key_mask_add, int32_t B, int32_t Lq, int32_t Lk, int32_t heads, int32_t head_dim, void* ctx,
+                        int64_t ld_ctx, int32_t ctx_mode, float* probs, void* cuda_stream);
 int vb200_self_attention(const void* qkv_bf16, int64_t ld_qkv, int32_t hidden, const float* mask_add, void* ctx_bf16,
                          int64_t ld_ctx, int32_t B, int32_t L, int32_t heads, int32_t head_dim, int32_t act_fp16,
                          void* cuda_stream);

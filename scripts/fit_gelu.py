@@ -23,13 +23,21 @@ for k, ck in enumerate(C.cheb2poly(c)):
     ps = P.polyadd(ps, ck * P.polypow([-1.0, 2.0], k))          # t = 2 s - 1, s = u / ZMAX^2
 d = [np.float32(ck / ZMAX ** (2 * k)) for k, ck in enumerate(ps)]
 print("coefficients of u^k:", ["%.9e" % v for v in d])
+def gelu_kernel(x):
+    """fp32 mirror of csrc/common.cuh gelu_erf: erf = clamp(z * P(min(z^2, 9)), -1, 1)."""
+    x = x.astype(np.float32)
+    zf = (x * np.float32(0.7071067811865476)).astype(np.float32)
+    u = np.minimum((zf * zf).astype(np.float32), np.float32(ZMAX * ZMAX))
+    acc = np.full_like(u, d[-1])
+    for ck in d[-2::-1]:
+        acc = (acc * u + ck).astype(np.float32)
+    e = np.clip((zf * acc).astype(np.float32), np.float32(-1), np.float32(1))
+    hx = (x * np.float32(0.5)).astype(np.float32)
+    return (hx * e + hx).astype(np.float32)
+
+
 x = np.linspace(-10, 10, 800001).astype(np.float32)
-zf = np.clip(x * np.float32(0.7071067811865476), np.float32(-ZMAX), np.float32(ZMAX)).astype(np.float32)
-u = (zf * zf).astype(np.float32)
-acc = np.full_like(u, d[-1])
-for ck in d[-2::-1]:
-    acc = (acc * u + ck).astype(np.float32)
-hx = (x * np.float32(0.5)).astype(np.float32)
-g = (hx * (zf * acc).astype(np.float32) + hx).astype(np.float32)
 xe = x.astype(np.float64)
-print("max |gelu error|:", np.abs(g - 0.5 * xe * (1 + erf(xe / np.sqrt(2)))).max())
+print("max |gelu error| on [-10, 10]:", np.abs(gelu_kernel(x) - 0.5 * xe * (1 + erf(xe / np.sqrt(2)))).max())
+far = np.array([-1e4, -100.0, -50.0, -6.0, 6.0, 50.0, 100.0, 1e4], dtype=np.float32)
+print("far from the origin:", dict(zip(far.tolist(), gelu_kernel(far).tolist())))

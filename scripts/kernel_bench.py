@@ -51,7 +51,11 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="0 persistent kernel, 1 one-tile-per-CTA kernel")
     ap.add_argument("--stamps", action="store_true", help="print clock64 phase stamps of the persistent kernel")
     ap.add_argument("--bn", type=int, default=0, help="override block_n of every plain GEMM")
+    ap.add_argument("--debug", default="0", help="VB200_DEBUG timing decomposition (comma list, each timed in turn): "
+                                                 "1 no MMA, 2 no stores, 4 no operand loads")
     a = ap.parse_args()
+    debug_modes = [int(x) for x in str(a.debug).split(",")]
+    only = [x for x in a.only.split(",") if x]
     lib = L.load()
     B, T, V = a.batch, 31, 36
     Mt, Mv = B * T, B * V
@@ -73,7 +77,7 @@ def main():
     ]
     res = []
     for name, M, N, K, actf, ln, bn in gemms:
-        if a.only and a.only not in name:
+        if only and not any(o == name or (o.endswith("*") and o[:-1] in name) for o in only):
             continue
         if a.variant == 2 and (ln or N % 128 or M < 256):
             continue
@@ -97,43 +101,45 @@ def main():
             rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
                                   ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, None, C.c_void_p(cur()))
             L.check(rc, None)
-        us = time_graph(run, a.reps)
-        fl = 2.0 * M * N * K
-        res.append(dict(kernel=name, M=M, N=N, K=K, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
-        print(json.dumps(res[-1]), flush=True)
-        if a.stamps and a.variant in (0, 2):
-            tb = torch.zeros(16 * 4096, dtype=torch.int64, device="cuda")
-            x, w, b, r, ga, be, yb, yf, ldf = sets[0]
-            rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
-                                  ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, ptr(tb), C.c_void_p(cur()))
-            L.check(rc, None)
-            torch.cuda.synchronize()
-            t = tb.view(-1, 16).cpu()
-            t = t[t[:, 0] != 0]
-            d = (t - t[:, :1]).double()
-            names = ["entry", "setup", "first_kblock", "mma_issued", "acc_ready", "epi_pass1", "ln_exchange", "epi_done",
-                     "c0_ld", "c0_res", "c0_math", "c0_store", "c1_ld", "c1_res", "c1_math", "c1_store"]
-            print("   stamps (SM cycles since CTA entry, median over %d CTAs): " % len(t) +
-                  ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names[:8]) if (t[:, i] != 0).any()), flush=True)
-            lead = t[t[:, 11] != 0]
-            if len(lead):
-                nkb = (K + 63) // 64
-                per = ((lead[:, 10] - lead[:, 2]).double() / (lead[:, 11].double() * nkb))
-                print(f"   steady state: {len(lead)} MMA-issuing CTAs, tiles/CTA median {int(lead[:, 11].median())}, "
-                      f"cycles per k-block median {per.median():.0f} (min {per.min():.0f} max {per.max():.0f}); "
-                      f"producer done {int((t[:, 12] - t[:, 0]).double().median())}, mma done {int((lead[:, 10] - lead[:, 0]).double().median())}, "
-                      f"epilogue done {int((t[:, 13] - t[:, 0]).double().median())}", flush=True)
-            if (t[:, 14] != 0).any():
-                print(f"   epilogue of warp 2: acc_ready -> first chunk loaded {int((t[:, 14] - t[:, 4]).double().median())}, "
-                      f"-> first chunk stored {int((t[:, 15] - t[:, 4]).double().median())}, -> done {int((t[:, 7] - t[:, 4]).double().median())}", flush=True)
-            g0, g1 = t[:, 8].double(), t[:, 9].double()
-            print(f"   globaltimer: kernel span {(g1.max() - g0.min()) / 1e3:.2f} us, CTA start spread {(g0.max() - g0.min()) / 1e3:.2f} us, "
-                  f"CTA lifetime median {(g1 - g0).median() / 1e3:.2f} us max {(g1 - g0).max() / 1e3:.2f} us, "
-                  f"end spread {(g1.max() - g1.min()) / 1e3:.2f} us", flush=True)
+        for dbg in debug_modes:
+            os.environ["VB200_DEBUG"] = str(dbg)
+            us = time_graph(run, a.reps)
+            fl = 2.0 * M * N * K
+            res.append(dict(kernel=name, M=M, N=N, K=K, debug=dbg, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
+            print(json.dumps(res[-1]), flush=True)
+            if a.stamps and a.variant in (0, 2):
+                tb = torch.zeros(16 * 4096, dtype=torch.int64, device="cuda")
+                x, w, b, r, ga, be, yb, yf, ldf = sets[0]
+                rc = lib.vb200_linear(ptr(x), K, ptr(w), K, ptr(b), ptr(r), N if ln else 0, ptr(ga), ptr(be), 1e-12, actf,
+                                      ptr(yb), N, ptr(yf), ldf, M, N, K, bn, 0, f16, a.variant, ptr(tb), C.c_void_p(cur()))
+                L.check(rc, None)
+                torch.cuda.synchronize()
+                t = tb.view(-1, 16).cpu()
+                t = t[t[:, 0] != 0]
+                d = (t - t[:, :1]).double()
+                names = ["entry", "setup", "first_kblock", "mma_issued", "acc_ready", "epi_pass1", "ln_exchange", "epi_done",
+                         "c0_ld", "c0_res", "c0_math", "c0_store", "c1_ld", "c1_res", "c1_math", "c1_store"]
+                print("   stamps (SM cycles since CTA entry, median over %d CTAs): " % len(t) +
+                      ", ".join(f"{n}={int(d[:, i].median())}" for i, n in enumerate(names[:8]) if (t[:, i] != 0).any()), flush=True)
+                lead = t[t[:, 11] != 0]
+                if len(lead):
+                    nkb = (K + 63) // 64
+                    per = ((lead[:, 10] - lead[:, 2]).double() / (lead[:, 11].double() * nkb))
+                    print(f"   steady state: {len(lead)} MMA-issuing CTAs, tiles/CTA median {int(lead[:, 11].median())}, "
+                          f"cycles per k-block median {per.median():.0f} (min {per.min():.0f} max {per.max():.0f}); "
+                          f"producer done {int((t[:, 12] - t[:, 0]).double().median())}, mma done {int((lead[:, 10] - lead[:, 0]).double().median())}, "
+                          f"epilogue done {int((t[:, 13] - t[:, 0]).double().median())}", flush=True)
+                if (t[:, 14] != 0).any():
+                    print(f"   epilogue of warp 2: acc_ready -> first chunk loaded {int((t[:, 14] - t[:, 4]).double().median())}, "
+                          f"-> first chunk stored {int((t[:, 15] - t[:, 4]).double().median())}, -> done {int((t[:, 7] - t[:, 4]).double().median())}", flush=True)
+                g0, g1 = t[:, 8].double(), t[:, 9].double()
+                print(f"   globaltimer: kernel span {(g1.max() - g0.min()) / 1e3:.2f} us, CTA start spread {(g0.max() - g0.min()) / 1e3:.2f} us, "
+                      f"CTA lifetime median {(g1 - g0).median() / 1e3:.2f} us max {(g1 - g0).max() / 1e3:.2f} us, "
+                      f"end spread {(g1.max() - g1.min()) / 1e3:.2f} us", flush=True)
 
     attn = [("self_attn_text", 12, 64, T), ("self_attn_img", 8, 128, V)]
     for name, heads, d, Lq in attn:
-        if a.only and a.only not in name:
+        if only and name not in only:
             continue
         H = heads * d
         qkv = torch.randn(B * Lq, 3 * H, generator=g, device="cuda").to(act)
@@ -144,7 +150,7 @@ def main():
             L.check(lib.vb200_self_attention(ptr(qkv), 3 * H, H, ptr(mask), ptr(ctx), H, B, Lq, heads, d, f16, C.c_void_p(cur())), None)
         us = time_graph(run, a.reps)
         print(json.dumps(dict(kernel=name, us=round(us, 2))), flush=True)
-    if not a.only or "co_attn" in a.only:
+    if not only or "co_attn" in only:
         H = 1024
         qi = torch.randn(Mv, 3 * H, generator=g, device="cuda").to(act)
         qt = torch.randn(Mt, 3 * H, generator=g, device="cuda").to(act)

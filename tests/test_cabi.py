@@ -30,15 +30,16 @@ def test_header_symbols_all_exported():
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vb200_abi_version() == 1
+    assert lib.vb200_abi_version() == 2
 
 
 def test_ctypes_structs_match_header_layout():
     # field order / sizes the header fixes (LP64)
     assert C.sizeof(L.Tensor) == 8 + 4 + 4 + 16 + 8
     assert C.sizeof(L.Inputs) == 16 + 8 * 8
-    assert C.sizeof(L.Outputs) == 12 * 8
-    assert C.sizeof(L.Options) == 28
+    assert C.sizeof(L.Outputs) == 13 * 8
+    assert C.sizeof(L.Options) == 36
+    assert C.sizeof(L.RegionInputs) == 16 + 9 * 8
 
 
 def _create(cfg, sd, **opt):

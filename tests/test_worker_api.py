@@ -211,15 +211,58 @@ def test_prediction_batch_equals_one_request_at_a_time():
     for r in reqs[:-1]:
         single.append(W.prediction(*r))
     W.model = RowModel()
-    got = W.prediction_batch(reqs)
+    got = W.prediction_batch(reqs, bucket=1)
     assert len(W.model.calls) == 2                                    # one per (T, V) group
     assert sorted(c["B"] for c in W.model.calls) == [2, 14]          # 1 + filler + 2 + 4 + 1 + 1 + 2 + 1 = 13 -> even 14
-    big = max(W.model.calls, key=lambda c: c["B"])
-    assert big["select"] == (L.OUT_VIL_PREDICTION | L.OUT_VIL_BINARY_PREDICTION | L.OUT_VIL_LOGIT | L.OUT_VISION_LOGIT |
-                             L.OUT_VIL_TRI_PREDICTION | L.OUT_VIL_PREDICTION_GQA)
+    assert all(c["select"] == L.OUT_TASK_HEADS for c in W.model.calls)   # fixed select: one plan per shape, whatever is pending
+    W.model = RowModel()
+    got8 = W.prediction_batch(reqs)                                   # default: batches padded to multiples of 8
+    assert sorted(c["B"] for c in W.model.calls) == [8, 16]
+    for a, b in zip(got8[:-1], single):
+        _same(a, b)
     for a, b in zip(got[:-1], single):
         _same(a, b)
     assert isinstance(got[-1], AssertionError) and "2 images" in str(got[-1])
+
+
+def test_prediction_batch_nlvr2_pair_lands_on_even_row_after_even_sized_request(monkeypatch):
+    """task 1 (1 row), task 7 (2 rows), task 12: the filler must be ONE row so the pair starts at row 4, and the
+    binary logits must be those of the pair itself (compared as logits, not only as the top answer)."""
+    W.label_maps.update(vqa=None, gqa=None)
+    monkeypatch.setattr(W, "_decode", lambda task_id, out, spatials, infos: out)     # raw sliced outputs
+    for seed in range(6):
+        reqs = [_rand_req("1", 1, 9, 100 + seed), _rand_req("7", 2, 9, 200 + seed), _rand_req("12", 2, 9, 300 + seed),
+                _rand_req("7", 3, 9, 400 + seed), _rand_req("12", 2, 9, 500 + seed)]
+        W.model = RowModel()
+        single = [W.prediction(*r) for r in reqs]
+        for bucket in (1, 8):
+            W.model = RowModel()
+            got = W.prediction_batch(reqs, bucket=bucket)
+            for i in (2, 4):
+                assert got[i][3].shape == (1, 2)
+                assert torch.allclose(got[i][3], single[i][3], rtol=1e-4, atol=1e-4), (seed, bucket, i)
+            assert torch.allclose(got[1][2], single[1][2], rtol=1e-4, atol=1e-4)
+
+
+def test_micro_batch_worker_close_cancels_queued_messages():
+    import concurrent.futures as cf
+    W.label_maps.update(vqa=None, gqa=None)
+    W.model = RowModel()
+    W.tokenizer = W.WordpieceTokenizer(VOCAB)
+    worker = W.MicroBatchWorker(max_rows=4, max_wait_ms=1.0)
+    worker.close()
+    fut = worker.submit({"image_path": ["/m/demo/a.jpg"], "question": "what", "socket_id": "s", "task_id": "1"},
+                        [torch.rand(3, 2048)], [{"image_width": 4, "image_height": 4, "bbox": np.zeros((3, 4), dtype=np.float32)}])
+    with pytest.raises(cf.CancelledError):
+        fut.result(timeout=5)
+    # a message that slipped in behind the sentinel is cancelled by close() as well
+    worker2 = W.MicroBatchWorker(max_rows=4, max_wait_ms=1.0)
+    worker2._q.put(None)
+    late = cf.Future()
+    worker2._q.put(({"task_id": "1"}, [], [], late))
+    worker2.close()
+    with pytest.raises(cf.CancelledError):
+        late.result(timeout=5)
 
 
 def test_micro_batch_worker_round_trip():
@@ -260,5 +303,5 @@ def test_micro_batch_worker_round_trip():
         else:
             assert r["result"]["image_name_list"] == e["image_name_list"]
             assert r["result"]["confidence_list"] == pytest.approx(e["confidence_list"], abs=0.02)
-    # all five messages were pending together: ONE model call -- 1 + filler (NLVR2 onto an even row) + 2 + 3 + 1 rows
+    # all five messages were pending together: ONE model call -- 1 + filler (NLVR2 onto an even row) + 2 + 3 + 1 rows = 8
     assert [c["B"] for c in W.model.calls] == [8]

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvilbert_b200.so")
 
-VB200_ABI_VERSION = 1
+VB200_ABI_VERSION = 2
 F32, F16, BF16 = 0, 1, 2
 
 OUT_VIL_PREDICTION = 1 << 0
@@ -26,6 +26,7 @@ OUT_LINGUISIC_PREDICTION = 1 << 7
 OUT_LINGUISIC_LOGIT = 1 << 8
 OUT_TASK_HEADS = 0x15F
 OUT_ALL = 0x1FF
+OUT_ATTENTION = 1 << 9
 
 
 class Tensor(C.Structure):
@@ -42,7 +43,15 @@ class Inputs(C.Structure):
 
 OUTPUT_FIELDS = ["vil_prediction", "vil_prediction_gqa", "vil_logit", "vil_binary_prediction",
                  "vil_tri_prediction", "vision_prediction", "vision_logit", "linguisic_prediction",
-                 "linguisic_logit", "sequence_output_t", "sequence_output_v", "pooled_output"]
+                 "linguisic_logit", "sequence_output_t", "sequence_output_v", "pooled_output", "attention_probs"]
+
+
+class RegionInputs(C.Structure):
+    """vb200_region_inputs: custom_prediction()'s detector output (worker.py:422-455) instead of built tensors."""
+    _fields_ = [("batch", C.c_int32), ("n_tokens", C.c_int32), ("n_boxes", C.c_int32),
+                ("question", C.c_void_p), ("segment_ids", C.c_void_p), ("input_mask", C.c_void_p),
+                ("task_tokens", C.c_void_p), ("box_features", C.c_void_p), ("boxes", C.c_void_p),
+                ("image_wh", C.c_void_p), ("num_boxes", C.c_void_p), ("spatials_out", C.c_void_p)]
 
 
 class Outputs(C.Structure):
@@ -52,12 +61,14 @@ class Outputs(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_labels", C.c_int32), ("use_cuda_graph", C.c_int32),
                 ("use_pdl", C.c_int32), ("strict", C.c_int32), ("act_fp16", C.c_int32),
-                ("fused_layernorm", C.c_int32)]
+                ("fused_layernorm", C.c_int32), ("split_fp32", C.c_int32), ("max_plans", C.c_int32)]
 
 
 # every symbol include/vilbert_b200.h declares (tests/test_cabi.py checks the list against the header)
 EXPORTS = ["vb200_abi_version", "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_forward", "vb200_forward_slot",
-           "vb200_forward_host", "vb200_forward_host_slot", "vb200_plan_info", "vb200_model_dim", "vb200_profile_ops", "vb200_linear", "vb200_layernorm",
+           "vb200_forward_host", "vb200_forward_host_slot", "vb200_plan_info", "vb200_model_dim", "vb200_profile_ops",
+           "vb200_attention_layout", "vb200_forward_regions", "vb200_encode_text", "vb200_encode_image", "vb200_forward_cached",
+           "vb200_linear", "vb200_linear_split", "vb200_layernorm", "vb200_layernorm_split", "vb200_attention_f32",
            "vb200_self_attention", "vb200_co_attention"]
 
 _lib = None
@@ -94,6 +105,14 @@ def load():
     lib.vb200_model_dim.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     lib.vb200_profile_ops.argtypes = [vp, i32, i32, i32, u32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(i32)]
+    lib.vb200_attention_layout.argtypes = [vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    lib.vb200_forward_regions.argtypes = [vp, C.POINTER(RegionInputs), C.POINTER(Outputs), u32, i32, vp]
+    lib.vb200_encode_text.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.vb200_encode_image.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.vb200_forward_cached.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, C.POINTER(Outputs), u32, i32, vp]
+    lib.vb200_linear_split.argtypes = [vp, i64, vp, i64, vp, i32, vp, i64, vp, i64, i64, i64, i64, vp]
+    lib.vb200_layernorm_split.argtypes = [vp, i64, vp, i64, vp, vp, f32, vp, i64, vp, i64, i64, i64, vp]
+    lib.vb200_attention_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp, i32, i32, i32, i32, i32, vp, i64, i32, vp, vp]
     lib.vb200_linear.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, f32, i32, vp, i64, vp, i64,
                                  i64, i64, i64, i32, i32, i32, i32, vp, vp]
     lib.vb200_layernorm.argtypes = [vp, i64, vp, i64, vp, vp, f32, vp, i64, vp, i64, i64, i64, i32, vp]

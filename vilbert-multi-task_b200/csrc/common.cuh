@@ -248,13 +248,15 @@ __device__ __forceinline__ float erf_fast(float x) {
 }
 // GELU, erf form: x * 0.5 * (1 + erf(x / sqrt(2)))   ([UPSTREAM] vilbert.py `gelu`)
 __device__ __forceinline__ float gelu_erf_as(float x) { return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
-// Same function, 15 issue slots and no MUFU: erf(z) = z * P(z^2) on |z| <= 3 (minimax fit of degree 8 in z^2, |error| < 2.6e-5
-// in fp32 Horner form), z clamped to [-3, 3] (1 - erf(3) = 2.2e-5).  |gelu error| <= 6.6e-5 (at x = 4.24, value 4.24), i.e.
-// < 7 % of half an fp16 ulp there; the A&S form above is 30x more accurate but costs ~27 slots incl. 2 MUFU, and the FFN-in
-// epilogue is instruction-issue bound (16 K evaluations per 128x128 tile).  Coefficients: scripts/fit_gelu.py.
+// Same function, 16 issue slots and no MUFU: erf(z) = z * P(min(z^2, 9)) clamped to [-1, 1] (minimax fit of degree 8 in z^2 on
+// |z| <= 3, |error| < 2.6e-5 in fp32 Horner form; beyond |z| = 3 the product z * P(9) = z / 3.00007 leaves [-1, 1] and the clamp
+// returns erf = +-1 EXACTLY, so a strongly negative pre-activation gives -0 and a strongly positive one x itself -- the earlier
+// form clamped z instead and returned -1.1e-5 * x there).  |gelu error| <= 6.7e-5 (at x = 4.24, value 4.24), i.e. < 7 % of half
+// an fp16 ulp there; the A&S form above is 30x more accurate but costs ~27 slots incl. 2 MUFU, and the FFN-in epilogue is
+// instruction-issue bound (16 K evaluations per 128x128 tile).  Coefficients: scripts/fit_gelu.py.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
-    const float u = z * z;
+    const float z = x * 0.70710678118654752440f;
+    const float u = fminf(z * z, 9.0f);
     float p = 4.074150084e-08f;
     p = fmaf(p, u, -1.944801170e-06f);
     p = fmaf(p, u, 4.106021152e-05f);
@@ -264,8 +266,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
     p = fmaf(p, u, 1.110793054e-01f);
     p = fmaf(p, u, -3.753148615e-01f);
     p = fmaf(p, u, 1.128268480e+00f);
+    const float e = fminf(fmaxf(z * p, -1.0f), 1.0f);
     const float hx = 0.5f * x;
-    return fmaf(hx, z * p, hx);
+    return fmaf(hx, e, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -301,6 +304,16 @@ __device__ __forceinline__ uint32_t pack16x2_rt(float lo, float hi, int f16) {
     return pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ uint16_t cvt16_rt(float v, int f16) { return static_cast<uint16_t>(pack16x2_rt(v, 0.0f, f16) & 0xffffu); }
+
+// ---- fp32-parity mode ("fp32x"): a value x travels as TWO fp16 numbers hi = fp16(x), lo = fp16(x - hi) (22 significand bits;
+// lo may be an fp16 subnormal, which the tensor cores handle).  16-bit operand buffers then hold, per 64 logical columns,
+// 192 physical ones: hi | lo | hi for activations, hi | hi | lo for weights, so that an ordinary K' = 3K GEMM computes
+// hi.hi + lo.hi + hi.lo (the dropped lo.lo term is 2^-22 relative) with fp32 accumulation.
+__host__ __device__ __forceinline__ int split_col(int c) { return (c >> 6) * 192 + (c & 63); }   // column of the first hi
+__device__ __forceinline__ float split_hi(float x) {
+    return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)));
+}
+__device__ __forceinline__ float split_lo(float x) { return x - split_hi(x); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -17,7 +17,7 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
                   const float* __restrict__ task_tab, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                   float* __restrict__ mask_add, int B, int Tin, int H, int vocab, int max_pos, int n_type, int n_task,
-                  int task_tokens, int f16) {
+                  int task_tokens, int f16, int split16) {
     const int T = Tin + (task_tokens ? 1 : 0);
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -66,7 +66,7 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
     }
     const float rstd = 1.0f / sqrtf(warp_sum(sq) / static_cast<float>(H) + eps);
     float4* of = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * H);
-    uint2* ob = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * H);
+    uint2* ob = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * (split16 ? 3 * H : H));
     const float4* gp = reinterpret_cast<const float4*>(gamma);
     const float4* bp = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -79,7 +79,15 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
             y.z = (x[k].z - mean) * rstd * g.z + be.z;
             y.w = (x[k].w - mean) * rstd * g.w + be.w;
             of[lane + 32 * k] = y;
-            ob[lane + 32 * k] = make_uint2(pack16x2_rt(y.x, y.y, f16), pack16x2_rt(y.z, y.w, f16));
+            if (split16) {             // fp32-parity mode: fp16 hi | lo | hi per 64 columns (common.cuh split_col)
+                uint2* o3 = ob + split_col(4 * (lane + 32 * k)) / 4;
+                const uint2 hi = make_uint2(pack16x2_rt(y.x, y.y, 1), pack16x2_rt(y.z, y.w, 1));
+                o3[0] = hi;
+                o3[16] = make_uint2(pack16x2_rt(split_lo(y.x), split_lo(y.y), 1), pack16x2_rt(split_lo(y.z), split_lo(y.w), 1));
+                o3[32] = hi;
+            } else {
+                ob[lane + 32 * k] = make_uint2(pack16x2_rt(y.x, y.y, f16), pack16x2_rt(y.z, y.w, f16));
+            }
         }
     }
     if (lane == 0) {
@@ -95,30 +103,126 @@ text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ s
 // one block per (sample, region) row; F % 8 == 0, Kp % 8 == 0, Kp >= F + 8
 __global__ void __launch_bounds__(256)
 image_pack_kernel(const float* __restrict__ feats, const float* __restrict__ loc, const uint8_t* __restrict__ image_mask,
-                  __nv_bfloat16* __restrict__ a_out, float* __restrict__ mask_add, int F, int Kp, int f16) {
+                  __nv_bfloat16* __restrict__ a_out, float* __restrict__ mask_add, int F, int Kp, int f16, int split16) {
     const int row = blockIdx.x;
     const float4* src = reinterpret_cast<const float4*>(feats + static_cast<size_t>(row) * F);
-    uint4* dst = reinterpret_cast<uint4*>(a_out + static_cast<size_t>(row) * Kp);
+    uint4* dst = reinterpret_cast<uint4*>(a_out + static_cast<size_t>(row) * (split16 ? 3 * Kp : Kp));
     const int nvec = F / 8;
+    // 8 columns [8i, 8i+8) -> one 16-byte store; fp32-parity mode: fp16 hi | lo | hi per 64 columns (split_col), three stores
+    auto put = [&](int i, float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3) {
+        uint4 u;
+        u.x = pack16x2_rt(a0, a1, f16); u.y = pack16x2_rt(a2, a3, f16);
+        u.z = pack16x2_rt(b0, b1, f16); u.w = pack16x2_rt(b2, b3, f16);
+        if (!split16) { dst[i] = u; return; }
+        uint4* d3 = dst + split_col(8 * i) / 8;
+        uint4 l;
+        l.x = pack16x2_rt(split_lo(a0), split_lo(a1), 1); l.y = pack16x2_rt(split_lo(a2), split_lo(a3), 1);
+        l.z = pack16x2_rt(split_lo(b0), split_lo(b1), 1); l.w = pack16x2_rt(split_lo(b2), split_lo(b3), 1);
+        d3[0] = u; d3[8] = l; d3[16] = u;
+    };
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);   // streamed once
-        uint4 u;
-        u.x = pack16x2_rt(a.x, a.y, f16); u.y = pack16x2_rt(a.z, a.w, f16);
-        u.z = pack16x2_rt(b.x, b.y, f16); u.w = pack16x2_rt(b.z, b.w, f16);
-        dst[i] = u;
+        put(i, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
     }
     const int tail_vec = (Kp - F) / 8;
     if (threadIdx.x < tail_vec) {
-        uint4 u = make_uint4(0, 0, 0, 0);
         if (threadIdx.x == 0) {
             const float* l = loc + static_cast<size_t>(row) * 5;
-            u.x = pack16x2_rt(l[0], l[1], f16);
-            u.y = pack16x2_rt(l[2], l[3], f16);
-            u.z = pack16x2_rt(l[4], 0.0f, f16);
+            put(nvec, l[0], l[1], l[2], l[3], l[4], 0.0f, 0.0f, 0.0f);
+        } else {
+            put(nvec + threadIdx.x, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
         }
-        dst[nvec + threadIdx.x] = u;
     }
     if (threadIdx.x == 0) mask_add[row] = (1.0f - static_cast<float>(image_mask[row])) * -10000.0f;
+}
+
+// custom_prediction()'s input builder on the device (worker.py:422-455): per image, the detector's n box features [n, F] become the
+// GEMM operand rows [global mean row | box rows] (fp32 -> 16-bit, straight into the image-embedding GEMM's A buffer -- the fp32
+// [n+1, F] tensor the reference builds with cat/stack is never materialised), pixel boxes become the 5-d normalised locations
+// (x1/w, y1/h, x2/w, y2/h, area/(w h); global row 0,0,1,1,1), masks are set.  num_boxes (optional) marks padded boxes per image:
+// they are excluded from the mean, written as zeros and masked.
+// grid (B, ceil(F / 1024) + 1): the last grid row writes the location columns, the masks and the optional spatials copy.
+__global__ void __launch_bounds__(128)
+region_pack_kernel(const float* __restrict__ box_feats, const float* __restrict__ boxes, const float* __restrict__ image_wh,
+                   const int32_t* __restrict__ num_boxes, __nv_bfloat16* __restrict__ a_out, float* __restrict__ mask_add,
+                   float* __restrict__ spatials_out, int n, int F, int Kp, int f16, int split16) {
+    const int b = blockIdx.x, V = n + 1;
+    int nb = num_boxes ? num_boxes[b] : n;
+    nb = nb < 0 ? 0 : (nb > n ? n : nb);
+    const size_t ld = static_cast<size_t>(split16 ? 3 * Kp : Kp);
+    auto put = [&](int row, int i, const float (&x)[8]) {           // 8 columns [8i, 8i+8) of operand row `row`
+        uint4* dst = reinterpret_cast<uint4*>(a_out + static_cast<size_t>(row) * ld);
+        uint4 u;
+        u.x = pack16x2_rt(x[0], x[1], f16); u.y = pack16x2_rt(x[2], x[3], f16);
+        u.z = pack16x2_rt(x[4], x[5], f16); u.w = pack16x2_rt(x[6], x[7], f16);
+        if (!split16) { dst[i] = u; return; }
+        uint4* d3 = dst + split_col(8 * i) / 8;
+        uint4 l;
+        l.x = pack16x2_rt(split_lo(x[0]), split_lo(x[1]), 1); l.y = pack16x2_rt(split_lo(x[2]), split_lo(x[3]), 1);
+        l.z = pack16x2_rt(split_lo(x[4]), split_lo(x[5]), 1); l.w = pack16x2_rt(split_lo(x[6]), split_lo(x[7]), 1);
+        d3[0] = u; d3[8] = l; d3[16] = u;
+    };
+    if (blockIdx.y + 1 < gridDim.y) {
+        const int i = blockIdx.y * blockDim.x + threadIdx.x;           // 8-column group
+        if (i * 8 >= F) return;
+        float sum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        const float* src = box_feats + static_cast<size_t>(b) * n * F + i * 8;
+        for (int r = 0; r < n; ++r) {
+            float x[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (r < nb) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * F));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * F) + 1);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum[j] += x[j];
+            }
+            put(b * V + r + 1, i, x);
+        }
+        const float cnt = static_cast<float>(nb > 0 ? nb : 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[j] = sum[j] / cnt;              // torch.sum(feature, dim=0) / num_boxes (worker.py:432)
+        put(b * V, i, sum);
+        return;
+    }
+    const float w = image_wh[2 * b], h = image_wh[2 * b + 1];
+    const float wh = static_cast<float>(static_cast<double>(w) * static_cast<double>(h));     // float(image_w) * float(image_h)
+    const int tail_groups = (Kp - F) / 8;
+    for (int r = threadIdx.x; r < V; r += blockDim.x) {
+        float loc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        const bool real = r == 0 || r - 1 < nb;
+        if (r == 0) { loc[2] = loc[3] = loc[4] = 1.0f; }               // g_location = [0, 0, 1, 1, 1] (worker.py:443)
+        else if (real) {
+            const float* bx = boxes + (static_cast<size_t>(b) * n + (r - 1)) * 4;
+            const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+            loc[4] = (y2 - y1) * (x2 - x1) / wh;                       // computed before the coordinates are normalised (worker.py:438)
+            loc[0] = x1 / w; loc[1] = y1 / h; loc[2] = x2 / w; loc[3] = y2 / h;
+        }
+        const float zero[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        for (int g = 0; g < tail_groups; ++g) {
+            if (g == 0) put(b * V + r, F / 8, loc); else put(b * V + r, F / 8 + g, zero);
+        }
+        mask_add[b * V + r] = real ? 0.0f : -10000.0f;
+        if (spatials_out)
+            for (int j = 0; j < 5; ++j) spatials_out[(static_cast<size_t>(b) * V + r) * 5 + j] = loc[j];
+    }
+}
+
+// Retrieval reuse: row block `idx[b]` of a cached per-caption / per-image encoder state -> sample b of the pair plan's buffers
+// (fp32 residual stream, 16-bit GEMM operand, additive mask).  One CTA per destination sample; 16-byte copies.
+__global__ void __launch_bounds__(256)
+gather_state_kernel(const int32_t* __restrict__ idx, int n_src, const float* __restrict__ src_f32, const uint16_t* __restrict__ src_16,
+                    const float* __restrict__ src_mask, float* __restrict__ dst_f32, uint16_t* __restrict__ dst_16,
+                    float* __restrict__ dst_mask, int L, int n32 /* uint4 per sample, fp32 */, int n16 /* uint4 per sample, 16-bit */) {
+    const int b = blockIdx.x;
+    int s = idx[b];
+    s = s < 0 ? 0 : (s >= n_src ? n_src - 1 : s);
+    const uint4* a = reinterpret_cast<const uint4*>(src_f32) + static_cast<size_t>(s) * n32;
+    uint4* d = reinterpret_cast<uint4*>(dst_f32) + static_cast<size_t>(b) * n32;
+    for (int i = threadIdx.x; i < n32; i += blockDim.x) d[i] = a[i];
+    const uint4* a2 = reinterpret_cast<const uint4*>(src_16) + static_cast<size_t>(s) * n16;
+    uint4* d2 = reinterpret_cast<uint4*>(dst_16) + static_cast<size_t>(b) * n16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) d2[i] = a2[i];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) dst_mask[static_cast<size_t>(b) * L + i] = src_mask[static_cast<size_t>(s) * L + i];
 }
 
 // one warp per row; n_out <= 4
@@ -153,20 +257,37 @@ cudaError_t launch_text_embed(const int64_t* ids, const int64_t* seg, const int6
                               const float* word, const float* pos, const float* type, const float* task_tab,
                               const float* gamma, const float* beta, float eps, float* out_f32,
                               __nv_bfloat16* out_bf16, float* mask_add, int B, int Tin, int H, int vocab, int max_pos,
-                              int n_type, int n_task, int task_tokens, int f16, cudaStream_t st) {
-    if (H % 128 != 0 || H / 128 > kMaxVec) return cudaErrorInvalidValue;
+                              int n_type, int n_task, int task_tokens, int f16, int split16, cudaStream_t st) {
+    if (H % 128 != 0 || H / 128 > kMaxVec || (split16 && !f16)) return cudaErrorInvalidValue;
     const int T = Tin + (task_tokens ? 1 : 0);
     const int rows = B * T;
     text_embed_kernel<<<(rows + 3) / 4, 128, 0, st>>>(ids, seg, input_mask, task, word, pos, type, task_tab, gamma, beta,
                                                       eps, out_f32, out_bf16, mask_add, B, Tin, H, vocab, max_pos,
-                                                      n_type, n_task, task_tokens, f16);
+                                                      n_type, n_task, task_tokens, f16, split16);
     return cudaGetLastError();
 }
 
 cudaError_t launch_image_pack(const float* feats, const float* loc, const uint8_t* image_mask, __nv_bfloat16* a_out,
-                              float* mask_add, int rows, int F, int Kp, int f16, cudaStream_t st) {
-    if (F % 8 != 0 || Kp % 8 != 0 || Kp < F + 8 || (Kp - F) / 8 > 256) return cudaErrorInvalidValue;
-    image_pack_kernel<<<rows, 256, 0, st>>>(feats, loc, image_mask, a_out, mask_add, F, Kp, f16);
+                              float* mask_add, int rows, int F, int Kp, int f16, int split16, cudaStream_t st) {
+    if (F % 8 != 0 || Kp % 8 != 0 || Kp < F + 8 || (Kp - F) / 8 > 256 || (split16 && (!f16 || (Kp & 63)))) return cudaErrorInvalidValue;
+    image_pack_kernel<<<rows, 256, 0, st>>>(feats, loc, image_mask, a_out, mask_add, F, Kp, f16, split16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_region_pack(const float* box_feats, const float* boxes, const float* image_wh, const int32_t* num_boxes,
+                               __nv_bfloat16* a_out, float* mask_add, float* spatials_out, int B, int n, int F, int Kp, int f16,
+                               int split16, cudaStream_t st) {
+    if (B < 1 || n < 1 || F % 8 != 0 || Kp % 8 != 0 || Kp < F + 8 || (split16 && (!f16 || (Kp & 63)))) return cudaErrorInvalidValue;
+    const dim3 grid(B, (F / 8 + 127) / 128 + 1);
+    region_pack_kernel<<<grid, 128, 0, st>>>(box_feats, boxes, image_wh, num_boxes, a_out, mask_add, spatials_out, n, F, Kp, f16, split16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_state(const int32_t* idx, int n_src, const float* src_f32, const void* src_16, const float* src_mask,
+                                float* dst_f32, void* dst_16, float* dst_mask, int B, int L, int H, int H16, cudaStream_t st) {
+    if (B < 1 || n_src < 1 || (static_cast<long long>(L) * H) % 4 != 0 || (static_cast<long long>(L) * H16) % 8 != 0) return cudaErrorInvalidValue;
+    gather_state_kernel<<<B, 256, 0, st>>>(idx, n_src, src_f32, static_cast<const uint16_t*>(src_16), src_mask, dst_f32,
+                                           static_cast<uint16_t*>(dst_16), dst_mask, L, L * H / 4, L * H16 / 8);
     return cudaGetLastError();
 }
 

@@ -311,7 +311,7 @@ bool make_tmap_out(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
 // Decide whether a plain GEMM may use the TMA-store epilogue and build its output map (exactly one output, aligned).
 void setup_tma_store(CUtensorMap* tc, GemmEpilogue& e) {
     e.tma_store = 0;
-    if (e.split_k > 1 || e.gamma != nullptr) return;
+    if (e.split16 || e.gamma != nullptr) return;
     if (e.out_bf16 != nullptr && e.out_f32 == nullptr) {
         if (make_tmap_out(tc, e.out_bf16, e.M, e.N, e.ld_bf16, false, e.out_f16 != 0)) e.tma_store = 1;
     } else if (e.out_f32 != nullptr && e.out_bf16 == nullptr) {
@@ -321,7 +321,7 @@ void setup_tma_store(CUtensorMap* tc, GemmEpilogue& e) {
 
 // ------------------------------------------------------------------------------------------ launch list
 struct Op {
-    enum Kind { GEMM, SELF_ATTN, CO_ATTN, ROWDOT, LAYERNORM } kind;
+    enum Kind { GEMM, SELF_ATTN, CO_ATTN, ROWDOT, LAYERNORM, ATTN_F32 } kind;
     int stream = 0;                // 0 main, 1 side (image branch) inside the captured graph
     // GEMM
     CUtensorMap ta, tb, tc;        // operands, and the output (TMA-store epilogue, ep.tma_store != 0)
@@ -329,8 +329,12 @@ struct Op {
     int block_n = 128;
     bool ln = false;
     bool pair = false;             // CTA-pair kernel (cta_group::2); tb then has box rows block_n / 2
-    const void* w = nullptr;       // this GEMM's weight matrix (the previous GEMM of the stream prefetches it into L2)
-    long long w_bytes = 0;
+    // fp32 attention (attention_f32.cu): fp32-parity mode and the attention-probability output
+    const void *f_q = nullptr, *f_k = nullptr, *f_v = nullptr;
+    int f_ld_q = 0, f_ld_kv = 0, f_in = 0, f_Lq = 0, f_Lk = 0, f_ctx_mode = 0, f_ld_ctx = 0;
+    const float* f_mask = nullptr;
+    bf16* f_ctx = nullptr;
+    float* f_probs = nullptr;
     // attention
     const bf16 *qkv_a = nullptr, *qkv_b = nullptr;
     int ld_a = 0, ld_b = 0, hidden = 0;
@@ -351,8 +355,6 @@ struct Op {
     double flops = 0;
 };
 
-constexpr int kMaxSplitK = 3;   // fp32 partial-sum buffers of the split-K GEMMs that feed the row LayerNorm kernel
-
 struct OutBuf { float* p = nullptr; int rows = 0, cols = 0, ld = 0; };
 
 struct Plan {
@@ -368,6 +370,9 @@ struct Plan {
     int t_cur = 0, v_cur = 0;
     std::vector<Op> ops;
     OutBuf outs[12];
+    struct AttnOut { float* p; int heads, Lq, Lk; };   // attention probabilities [B, heads, Lq, Lk] in schedule order
+    std::vector<AttnOut> attn;                         //   (T / V layers: one entry; connection layers: text->image, image->text)
+    uint64_t last_use = 0;                             // plan-cache LRU stamp
     double flops = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -390,9 +395,7 @@ struct vb200_engine {
     vb200_options opt{};
     int num_labels = 0, gqa_labels = 0;
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
-    bool gemm_v1 = false;      // VB200_GEMM=v1: one-tile-per-CTA kernel (gemm_tcgen05.cu) instead of the persistent one
-    bool split_k_enabled = false;   // VB200_SPLITK=1 (see add_linear)
-    bool split_k_fixed = false;     // VB200_SPLITK=2
+    bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
     // batches in flight, per step: off 1.597-1.604 ms | full 1.567 | "mediumplus" (everything except edges across a fork / join)
@@ -405,8 +408,6 @@ struct vb200_engine {
     bool early_w = true;            // VB200_EARLYW=0: no weight loads ahead of griddepcontrol.wait
     bool pdl_gemm_gemm = false;     // VB200_PDL=mediumplus: also GEMM -> GEMM edges of one graph branch (FFN-in -> FFN-out)
     int light_pdl() const { return (pdl_light || opt.use_pdl) ? 1 : 0; }
-    bool weight_prefetch = false;   // VB200_PREFETCH=1: L2 prefetch of the next GEMM's weights from the idle epilogue warps
-                                    // (measured: 1.642 vs 1.629 ms per step -- the misses it hides are already overlapped)
     // CTA-pair GEMM (cta_group::2, gemm_pair.cu).  -1 = auto: 256-wide pair tiles where a GEMM has >= 4 waves of them (large
     // batches: +6 % at batch 512); below that the single-CTA kernel wins -- one or two tiles per CTA, where the pair's extra
     // cluster syncs and coarser tiles cost more than the halved W traffic saves (profiles/README.md).  VB200_PAIR=0|128|256
@@ -431,6 +432,8 @@ struct vb200_engine {
     float* lm_bias = nullptr;
     std::map<std::string, HostTensor> sd;
     std::map<std::vector<int64_t>, std::unique_ptr<Plan>> plans;
+    uint64_t use_clock = 0;         // LRU clock of the plan cache
+    size_t max_plans = 24;          // VB200_MAX_PLANS: least-recently-used plans beyond this are destroyed (workspace + graph)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<std::string> schedule;
@@ -493,6 +496,7 @@ struct vb200_engine {
             return L;
         }
         const bool f16 = opt.act_fp16 != 0;     // weights are stored in the same 16-bit format as the activations
+        if (x3) { load_linear_split(L, prefixes, n_each, k, extra_k_prefix, extra_k); return L; }
         std::vector<uint16_t> h(static_cast<size_t>(L.N) * L.ldw, 0);
         std::vector<float> hb(L.N, 0.0f);
         for (size_t pi = 0; pi < prefixes.size(); ++pi) {
@@ -524,6 +528,39 @@ struct vb200_engine {
         return L;
     }
     uint16_t cvt16(float f) const { return opt.act_fp16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); }
+    // fp32-parity mode: every weight is stored as fp16 hi | hi | lo per 64 columns of K (activations are hi | lo | hi), so the
+    // K' = 3K GEMM adds hi.hi + lo.hi + hi.lo; physical row stride 3 * ldw.
+    static void put_split_w(uint16_t* row, int64_t j, float w) {
+        const uint16_t hi = f32_to_f16_bits(w);
+        const uint16_t lo = f32_to_f16_bits(w - half_bits_to_f32(hi));
+        uint16_t* d = row + (j >> 6) * 192 + (j & 63);
+        d[0] = hi; d[64] = hi; d[128] = lo;
+    }
+    void load_linear_split(LinearW& L, const std::vector<std::string>& prefixes, int64_t n_each, int64_t k,
+                           const std::string& extra_k_prefix, int64_t extra_k) {
+        std::vector<uint16_t> h(static_cast<size_t>(L.N) * L.ldw * 3, 0);
+        std::vector<float> hb(L.N, 0.0f);
+        for (size_t pi = 0; pi < prefixes.size(); ++pi) {
+            HostTensor& w = need(prefixes[pi] + ".weight", 2, n_each, k);
+            HostTensor& b = need(prefixes[pi] + ".bias", 1, n_each);
+            for (int64_t n = 0; n < n_each; ++n) {
+                uint16_t* dst = &h[(pi * n_each + n) * L.ldw * 3];
+                for (int64_t j = 0; j < k; ++j) put_split_w(dst, j, w.at(n * k + j));
+                hb[pi * n_each + n] = b.at(n);
+            }
+        }
+        if (extra_k) {
+            HostTensor& w = need(extra_k_prefix + ".weight", 2, n_each, extra_k);
+            HostTensor& b = need(extra_k_prefix + ".bias", 1, n_each);
+            for (int64_t n = 0; n < n_each; ++n) {
+                for (int64_t j = 0; j < extra_k; ++j) put_split_w(&h[n * L.ldw * 3], k + j, w.at(n * extra_k + j));
+                hb[n] += b.at(n);
+            }
+        }
+        L.w = weights.alloc_n<bf16>(h.size());
+        CUDA_CHECK(cudaMemcpy(L.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+        L.bias = upload_f32(hb);
+    }
     LinearW load_linear1(const std::string& prefix, int64_t n, int64_t k) { return load_linear({prefix}, n, k); }
     RowW load_row(const std::string& prefix, int n_out, int k) {
         RowW r; r.n_out = n_out; r.K = k;
@@ -629,8 +666,13 @@ struct vb200_engine {
         {   // tied LM decoder: bf16 copy of the word-embedding table as a [vocab, hidden] GEMM operand
             HostTensor& w = need("bert.embeddings.word_embeddings.weight", 2, c.vocab, c.hidden);
             if (!dry) {
-                std::vector<uint16_t> h(static_cast<size_t>(c.vocab) * c.hidden);
-                for (size_t i = 0; i < h.size(); ++i) h[i] = cvt16(w.at(i));
+                std::vector<uint16_t> h(static_cast<size_t>(c.vocab) * c.hidden * (x3 ? 3 : 1));
+                if (x3) {
+                    for (int64_t n = 0; n < c.vocab; ++n)
+                        for (int64_t j = 0; j < c.hidden; ++j) put_split_w(&h[static_cast<size_t>(n) * c.hidden * 3], j, w.at(n * c.hidden + j));
+                } else {
+                    for (size_t i = 0; i < h.size(); ++i) h[i] = cvt16(w.at(i));
+                }
                 word_b16 = weights.alloc_n<bf16>(h.size());
                 CUDA_CHECK(cudaMemcpy(word_b16, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
             }
@@ -665,57 +707,45 @@ struct vb200_engine {
     //   fused_ln:  a single cluster-LayerNorm GEMM (epilogue normalises across the N tiles of a cluster)
     //   default :  GEMM (+bias, +activation) writing fp32 to the stream's scratch, then the row LayerNorm kernel
     //              (adds the residual) -- measured faster at every batch size tried (profiles/).
+    // All sizes are LOGICAL (elements of the mathematical matrices).  In fp32-parity mode (x3) every 16-bit operand buffer is
+    // physically 3x as wide (fp16 hi | lo | hi per 64 columns), so operand strides, the contraction length and the 16-bit
+    // output stride are multiplied by S = 3 here and nowhere else.
     void add_linear(Plan& pl, const bf16* A, int64_t a_rows, int64_t lda, const LinearW& W, int act, const float* res, int ld_res,
                     const LNW* ln, bf16* out_b, int ld_b, float* out_f, int ld_f, int stream = 0, Op::Sync sync = Op::NONE,
                     const float* mul = nullptr, int ld_mul = 0) {
+        const int S = x3 ? 3 : 1;
         const bool split_ln = ln != nullptr && !fused_ln;
+        if (x3 && act == vb::kActGelu) act = vb::kActGeluExact;
         Op op{};
         op.kind = Op::GEMM;
         op.stream = stream;
         op.sync = sync;
         op.ln = ln != nullptr && !split_ln;
-        op.block_n = gemm_v1 ? vb::gemm_pick_block_n(W.N, op.ln) : vb::gemm_p_pick_block_n(W.N, op.ln);
+        op.block_n = vb::gemm_p_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
-        if (!gemm_v1 && !op.ln && a_rows >= 256) {
+        if (!x3 && !op.ln && a_rows >= 256) {
             if (pair_bn > 0) op.pair = W.N % pair_bn == 0;
             else if (pair_bn < 0) op.pair = W.N % 256 == 0 && ((a_rows + 255) / 256) * (W.N / 256) >= 4 * (vb::num_sms_host() / 2);
             if (op.pair) op.block_n = pair_bn > 0 ? pair_bn : 256;
         }
-        op.ta = make_tmap(A, a_rows, W.ldw, lda, 128, opt.act_fp16 != 0);
-        op.tb = make_tmap(W.w, W.N, W.ldw, W.ldw, op.pair ? op.block_n / 2 : op.block_n, opt.act_fp16 != 0);
+        op.ta = make_tmap(A, a_rows, static_cast<int64_t>(W.ldw) * S, lda * S, 128, opt.act_fp16 != 0);
+        op.tb = make_tmap(W.w, W.N, static_cast<int64_t>(W.ldw) * S, static_cast<int64_t>(W.ldw) * S, op.pair ? op.block_n / 2 : op.block_n,
+                          opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
-        e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw;
+        e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw * S;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : (opt.use_pdl ? (early_w ? 5 : 1) : 0);
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
-        int split_k = 1;
         if (split_ln) {
-            float* y = pl.y_scratch[stream];
-            e.out_f32 = y; e.ld_f32 = W.N;
-            // Few tiles and a long K (FFN-out: K = 3072, 96 tiles at batch 64): cut K so ~2 CTAs per SM run short main loops;
-            // the LayerNorm kernel that follows sums the fp32 partials for free (it reads y anyway).
-            const long long tiles = ((a_rows + 127) / 128) * ((W.N + op.block_n - 1) / op.block_n);
-            const int num_kb = W.ldw / 64;
-            // Measured at batch 64: the isolated FFN-out GEMM gets 1.7x faster, but the whole step gets 7 % SLOWER -- the 96-CTA
-            // kernel left SMs to the other ViLBERT stream's kernels, the 288-CTA split version does not -- and a split that
-            // depends on the tile count would make results depend on the batch size (sharding is bit-exact today).
-            // Kept behind VB200_SPLITK=1 for large-K / single-stream use.
-            if (split_k_enabled && !gemm_v1 && !op.pair && act == vb::kActNone && num_kb >= 24 && tiles < 148) {
-                split_k = static_cast<int>(std::min<long long>(kMaxSplitK, std::max<long long>(1, 296 / tiles)));
-                while (split_k > 1 && num_kb / split_k < 6) --split_k;
-            }
-            // VB200_SPLITK=2: a split that depends on K only (K >= 2048 -> two halves), so results stay independent of the batch
-            if (split_k_fixed && !gemm_v1 && !op.pair && act == vb::kActNone && num_kb >= 32 && tiles <= 2 * 148) split_k = 2;
-            e.split_k = split_k;
-            e.split_stride = static_cast<long long>(a_rows) * W.N;
+            e.out_f32 = pl.y_scratch[stream]; e.ld_f32 = W.N;
         } else {
             e.res = res; e.ld_res = ld_res;
             e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr;
-            e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f;
+            e.out_bf16 = out_b; e.ld_bf16 = ld_b * S; e.out_f32 = out_f; e.ld_f32 = ld_f;
+            e.split16 = (x3 && out_b != nullptr) ? 1 : 0;
+            if (e.split16 && (W.N & 63)) fail(VB200_ERR_INVALID, "fp32-parity mode: 16-bit GEMM output of width %d is not a multiple of 64", W.N);
         }
-        if (tma_store_enabled && !gemm_v1 && !op.pair && !op.ln) setup_tma_store(&op.tc, e);
+        if (tma_store_enabled && !op.pair && !op.ln) setup_tma_store(&op.tc, e);
         op.flops = 2.0 * a_rows * W.N * W.K;
-        op.w = W.w;
-        op.w_bytes = static_cast<long long>(W.N) * W.ldw * 2;
         pl.flops += op.flops;
         pl.ops.push_back(op);
         if (split_ln) {
@@ -724,11 +754,29 @@ struct vb200_engine {
             l.stream = stream;
             l.ln_y = pl.y_scratch[stream]; l.ln_res = res; l.ld_x = ld_res;
             l.ln_g = ln->g; l.ln_b = ln->b; l.ln_out_f = out_f; l.ln_out_h = out_b; l.ln_ld = W.N;
-            l.ld_out = out_f ? ld_f : 0; l.ld_a = out_b ? ld_b : 0;
+            l.ld_out = out_f ? ld_f : 0; l.ld_a = out_b ? ld_b * S : 0;
             l.ln_M = static_cast<int>(a_rows); l.ln_N = W.N;
-            l.n_out = split_k;                                  // number of fp32 partials to sum
             pl.ops.push_back(l);
         }
+    }
+    // softmax(Q K^T / sqrt(d) + mask) V of one stream (self) or one direction of a connection layer.  Default: the tensor-core
+    // kernel writes the context (callers push that op themselves); this adds the fp32 kernel -- as THE attention in fp32-parity
+    // mode (context out as hi | lo | hi), and/or as the producer of the attention-probability output.
+    void add_attn_f32(Plan& pl, const void* q, int ld_q, const void* k, const void* v, int ld_kv, const float* mask, int Lq, int Lk,
+                      int heads, int hid, bf16* ctx, bool want_probs, int stream) {
+        Op a{};
+        a.kind = Op::ATTN_F32;
+        a.stream = stream;
+        a.f_q = q; a.f_k = k; a.f_v = v; a.f_ld_q = ld_q; a.f_ld_kv = ld_kv; a.f_mask = mask; a.f_Lq = Lq; a.f_Lk = Lk;
+        a.f_in = x3 ? 0 : (opt.act_fp16 ? 1 : 2);
+        a.B = pl.B; a.heads = heads; a.head_dim = hid / heads;
+        a.f_ctx = x3 ? ctx : nullptr; a.f_ctx_mode = x3 ? 3 : 0; a.f_ld_ctx = x3 ? 3 * hid : 0;
+        if (want_probs) {
+            a.f_probs = pl.mem.alloc_n<float>(static_cast<size_t>(pl.B) * heads * Lq * Lk);
+            pl.attn.push_back(Plan::AttnOut{a.f_probs, heads, Lq, Lk});
+        }
+        if (x3) { a.flops = 4.0 * pl.B * heads * Lq * Lk * (hid / heads); pl.flops += a.flops; }
+        pl.ops.push_back(a);
     }
     Op rowdot_op(const float* x, int ld_x, const RowW& w, const float* add, float* out, int ld_out, int M) {
         Op op{};
@@ -744,12 +792,20 @@ struct vb200_engine {
         return o;
     }
 
-    Plan* get_plan(int B, int Tin, int V, uint32_t select, int slot = 0) {
+    // Plan modes.  FULL is the reference's forward (worker.py:286-289).  The other three split it at the first connection layer
+    // for caption-image retrieval: everything before it depends on the caption alone (text embeddings +
+    // the text layers scheduled ahead of C0) or on the image alone (image embedding + any image layer ahead of C0), so a
+    // 1000 x 1000 score matrix computes those once per caption / per image and runs only the SUFFIX per pair -- the same kernels on
+    // the same rows, hence bit-identical scores.
+    enum PlanMode { FULL = 0, TEXT_PREFIX = 1, IMAGE_PREFIX = 2, SUFFIX = 3 };
+
+    Plan* get_plan(int B, int Tin, int V, uint32_t select, int slot = 0, int mode = FULL, bool want_attn = false) {
         if (slot < 0 || slot > 15) fail(VB200_ERR_INVALID, "slot %d out of range (0..15)", slot);
         if (slot > 0 && !opt.use_cuda_graph) fail(VB200_ERR_INVALID, "concurrent slots need CUDA-graph plans (use_cuda_graph)");
-        std::vector<int64_t> key{B, Tin, V, static_cast<int64_t>(select), slot};
+        if (mode == TEXT_PREFIX || mode == IMAGE_PREFIX) { select = 0; want_attn = false; }
+        std::vector<int64_t> key{B, Tin, V, static_cast<int64_t>(select), slot, mode, want_attn ? 1 : 0};
         auto it = plans.find(key);
-        if (it != plans.end()) return it->second.get();
+        if (it != plans.end()) { it->second->last_use = ++use_clock; return it->second.get(); }
         std::unique_ptr<Plan> up(new Plan());
         Plan& pl = *up;
         const Config& c = cfg;
@@ -759,70 +815,105 @@ struct vb200_engine {
         if (Tin > c.max_pos) fail(VB200_ERR_INVALID, "n_tokens %d exceeds max_position_embeddings %d", Tin, c.max_pos);
         pl.B = B; pl.Tin = Tin; pl.T = T; pl.V = V; pl.select = select;
         const int Mt = B * T, Mv = B * V, H = c.hidden, Hv = c.v_hidden, Hb = c.bi_hidden;
+        const size_t S = x3 ? 3 : 1;                 // physical width factor of the 16-bit operand buffers (fp32-parity mode)
+        const bool do_t = mode == FULL || mode == TEXT_PREFIX, do_v = mode == FULL || mode == IMAGE_PREFIX;
+        const bool do_s = mode == FULL || mode == SUFFIX;
         pl.kp = img_emb.ldw;
-        pl.img_a = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * pl.kp);
+        pl.img_a = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * pl.kp * S);
         pl.mask_t = pl.mem.alloc_n<float>(Mt);
         pl.mask_v = pl.mem.alloc_n<float>(Mv);
         for (int i = 0; i < 2; ++i) {
             pl.t_f32[i] = pl.mem.alloc_n<float>(static_cast<size_t>(Mt) * H);
-            pl.t_b16[i] = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * H);
+            pl.t_b16[i] = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * H * S);
             pl.v_f32[i] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv);
-            pl.v_b16[i] = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * Hv);
+            pl.v_b16[i] = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * Hv * S);
         }
         if (!fused_ln) {
             const size_t n0 = std::max({static_cast<size_t>(Mt) * H, static_cast<size_t>(Mv) * Hv, static_cast<size_t>(B) * 2 * Hb});
-            pl.y_scratch[0] = pl.mem.alloc_n<float>(n0 * kMaxSplitK);
-            pl.y_scratch[1] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv * kMaxSplitK);
+            pl.y_scratch[0] = pl.mem.alloc_n<float>(n0);
+            pl.y_scratch[1] = pl.mem.alloc_n<float>(static_cast<size_t>(Mv) * Hv);
         }
         const int qt = 3 * std::max(H, Hb), qv = 3 * std::max(Hv, Hb);
-        bf16* qkv_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * qt);
-        bf16* qkv_v = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * qv);
-        bf16* ctx_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * std::max(H, Hb));
-        bf16* ctx_v = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * std::max(Hv, Hb));
-        bf16* inter_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * c.inter);
-        bf16* inter_v = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * c.v_inter);
+        // Q | K | V projections: 16-bit for the tensor-core attention kernel, fp32 in fp32-parity mode
+        const size_t qe = x3 ? 4 : 2;
+        uint8_t* qkv_t = static_cast<uint8_t*>(pl.mem.alloc(static_cast<size_t>(Mt) * qt * qe));
+        uint8_t* qkv_v = static_cast<uint8_t*>(pl.mem.alloc(static_cast<size_t>(Mv) * qv * qe));
+        bf16* ctx_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * std::max(H, Hb) * S);
+        bf16* ctx_v = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * std::max(Hv, Hb) * S);
+        bf16* inter_t = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * c.inter * S);
+        bf16* inter_v = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * c.v_inter * S);
         auto& ops = pl.ops;
+        auto qkv_out = [&](uint8_t* q, bf16*& ob, float*& of) {       // where a QKV GEMM writes
+            ob = x3 ? nullptr : reinterpret_cast<bf16*>(q);
+            of = x3 ? reinterpret_cast<float*>(q) : nullptr;
+        };
+        auto qkv_at = [&](const uint8_t* q, int col) -> const void* { return q + static_cast<size_t>(col) * qe; };
 
         // ---- image embedding: LayerNorm(feat.W_img^T + loc.W_loc^T + b) as ONE GEMM over K = v_feat + 64
-        add_linear(pl, pl.img_a, Mv, pl.kp, img_emb, vb::kActNone, nullptr, 0, &vemb_ln, pl.v_b16[0], Hv, pl.v_f32[0], Hv,
-                   1);           // side stream: overlaps the text layers that precede the first co-attention
+        if (do_v)
+            add_linear(pl, pl.img_a, Mv, pl.kp, img_emb, vb::kActNone, nullptr, 0, &vemb_ln, pl.v_b16[0], Hv, pl.v_f32[0], Hv,
+                       1);           // side stream: overlaps the text layers that precede the first co-attention
         int tc = 0, vc = 0;
 
         auto single_layer = [&](const LayerW& L, int M, int hid, int inter, int heads, float** f32, bf16** b16, int& cur,
-                                bf16* qkv, bf16* ctx, bf16* inter_buf, const float* mask, int seq, int stream) {
-            add_linear(pl, b16[cur], M, hid, L.qkv, vb::kActNone, nullptr, 0, nullptr, qkv, 3 * hid, nullptr, 0, stream);
-            Op a{};
-            a.kind = Op::SELF_ATTN;
-            a.stream = stream;
-            a.qkv_a = qkv; a.ld_a = 3 * hid; a.hidden = hid; a.mask_a = mask; a.ctx_a = ctx; a.ld_ctx_a = hid;
-            a.B = B; a.La = seq; a.heads = heads; a.head_dim = hid / heads;
-            a.flops = 4.0 * B * heads * seq * seq * (hid / heads);
-            pl.flops += a.flops;
-            ops.push_back(a);
+                                uint8_t* qkv, bf16* ctx, bf16* inter_buf, const float* mask, int seq, int stream) {
+            bf16* qb; float* qf;
+            qkv_out(qkv, qb, qf);
+            add_linear(pl, b16[cur], M, hid, L.qkv, vb::kActNone, nullptr, 0, nullptr, qb, 3 * hid, qf, 3 * hid, stream);
+            if (!x3) {
+                Op a{};
+                a.kind = Op::SELF_ATTN;
+                a.stream = stream;
+                a.qkv_a = qb; a.ld_a = 3 * hid; a.hidden = hid; a.mask_a = mask; a.ctx_a = ctx; a.ld_ctx_a = hid;
+                a.B = B; a.La = seq; a.heads = heads; a.head_dim = hid / heads;
+                a.flops = 4.0 * B * heads * seq * seq * (hid / heads);
+                pl.flops += a.flops;
+                ops.push_back(a);
+            }
+            if (x3 || want_attn)
+                add_attn_f32(pl, qkv_at(qkv, 0), 3 * hid, qkv_at(qkv, hid), qkv_at(qkv, 2 * hid), 3 * hid, mask, seq, seq, heads, hid,
+                             ctx, want_attn, stream);
             add_linear(pl, ctx, M, hid, L.attn_out, vb::kActNone, f32[cur], hid, &L.ln1, b16[1 - cur], hid, f32[1 - cur], hid, stream);
             add_linear(pl, b16[1 - cur], M, hid, L.inter, vb::kActGelu, nullptr, 0, nullptr, inter_buf, inter, nullptr, 0, stream);
             add_linear(pl, inter_buf, M, inter, L.out, vb::kActNone, f32[1 - cur], hid, &L.ln2, b16[cur], hid, f32[cur], hid, stream);
         };
 
+        bool in_suffix = false;
         for (const std::string& step : schedule) {
             const int idx = atoi(step.c_str() + 1);
+            if (step[0] == 'C') in_suffix = true;
             if (step[0] == 'T') {
-                single_layer(t_layers[idx], Mt, H, c.inter, c.heads, pl.t_f32, pl.t_b16, tc, qkv_t, ctx_t, inter_t, pl.mask_t, T, 0);
+                if (in_suffix ? do_s : do_t)
+                    single_layer(t_layers[idx], Mt, H, c.inter, c.heads, pl.t_f32, pl.t_b16, tc, qkv_t, ctx_t, inter_t, pl.mask_t, T, 0);
             } else if (step[0] == 'V') {
-                single_layer(v_layers[idx], Mv, Hv, c.v_inter, c.v_heads, pl.v_f32, pl.v_b16, vc, qkv_v, ctx_v, inter_v, pl.mask_v, V, 1);
-            } else {
+                if (in_suffix ? do_s : do_v)
+                    single_layer(v_layers[idx], Mv, Hv, c.v_inter, c.v_heads, pl.v_f32, pl.v_b16, vc, qkv_v, ctx_v, inter_v, pl.mask_v, V, 1);
+            } else if (do_s) {
                 const ConnW& W = c_layers[idx];
-                add_linear(pl, pl.v_b16[vc], Mv, Hv, W.qkv_img, vb::kActNone, nullptr, 0, nullptr, qkv_v, 3 * Hb, nullptr, 0, 1);
-                add_linear(pl, pl.t_b16[tc], Mt, H, W.qkv_txt, vb::kActNone, nullptr, 0, nullptr, qkv_t, 3 * Hb, nullptr, 0, 0);
-                Op a{};
-                a.kind = Op::CO_ATTN;
-                a.sync = Op::JOIN;              // needs both projections
-                a.qkv_a = qkv_v; a.ld_a = 3 * Hb; a.qkv_b = qkv_t; a.ld_b = 3 * Hb; a.hidden = Hb;
-                a.mask_a = pl.mask_v; a.mask_b = pl.mask_t; a.ctx_a = ctx_t; a.ld_ctx_a = Hb; a.ctx_b = ctx_v; a.ld_ctx_b = Hb;
-                a.B = B; a.La = T; a.Lb = V; a.heads = c.bi_heads; a.head_dim = Hb / c.bi_heads;
-                a.flops = 8.0 * B * c.bi_heads * T * V * (Hb / c.bi_heads);
-                pl.flops += a.flops;
-                ops.push_back(a);
+                bf16 *qvb, *qtb; float *qvf, *qtf;
+                qkv_out(qkv_v, qvb, qvf);
+                qkv_out(qkv_t, qtb, qtf);
+                add_linear(pl, pl.v_b16[vc], Mv, Hv, W.qkv_img, vb::kActNone, nullptr, 0, nullptr, qvb, 3 * Hb, qvf, 3 * Hb, 1);
+                add_linear(pl, pl.t_b16[tc], Mt, H, W.qkv_txt, vb::kActNone, nullptr, 0, nullptr, qtb, 3 * Hb, qtf, 3 * Hb, 0);
+                const size_t first_co = ops.size();
+                if (!x3) {
+                    Op a{};
+                    a.kind = Op::CO_ATTN;
+                    a.qkv_a = qvb; a.ld_a = 3 * Hb; a.qkv_b = qtb; a.ld_b = 3 * Hb; a.hidden = Hb;
+                    a.mask_a = pl.mask_v; a.mask_b = pl.mask_t; a.ctx_a = ctx_t; a.ld_ctx_a = Hb; a.ctx_b = ctx_v; a.ld_ctx_b = Hb;
+                    a.B = B; a.La = T; a.Lb = V; a.heads = c.bi_heads; a.head_dim = Hb / c.bi_heads;
+                    a.flops = 8.0 * B * c.bi_heads * T * V * (Hb / c.bi_heads);
+                    pl.flops += a.flops;
+                    ops.push_back(a);
+                }
+                if (x3 || want_attn) {
+                    // text queries (Q2) over image keys / values (K1, V1) -> text context; then image queries (Q1) over K2, V2
+                    add_attn_f32(pl, qkv_at(qkv_t, 0), 3 * Hb, qkv_at(qkv_v, Hb), qkv_at(qkv_v, 2 * Hb), 3 * Hb, pl.mask_v, T, V,
+                                 c.bi_heads, Hb, ctx_t, want_attn, 0);
+                    add_attn_f32(pl, qkv_at(qkv_v, 0), 3 * Hb, qkv_at(qkv_t, Hb), qkv_at(qkv_t, 2 * Hb), 3 * Hb, pl.mask_t, V, T,
+                                 c.bi_heads, Hb, ctx_v, want_attn, 0);
+                }
+                ops[first_co].sync = Op::JOIN;              // needs both projections
                 // image branch (side stream; forks from the co-attention)
                 add_linear(pl, ctx_v, Mv, Hb, W.dense1, vb::kActNone, pl.v_f32[vc], Hv, &W.ln1, pl.v_b16[1 - vc], Hv, pl.v_f32[1 - vc], Hv, 1, Op::FORK);
                 add_linear(pl, pl.v_b16[1 - vc], Mv, Hv, W.v_inter, vb::kActGelu, nullptr, 0, nullptr, inter_v, c.v_inter, nullptr, 0, 1);
@@ -834,20 +925,62 @@ struct vb200_engine {
             }
         }
         pl.t_cur = tc; pl.v_cur = vc;
+        pl.outs[9] = OutBuf{pl.t_f32[tc], Mt, H, H};
+        pl.outs[10] = OutBuf{pl.v_f32[vc], Mv, Hv, Hv};
 
-        // ---- poolers + heads (main stream, after joining the image branch)
+        if (do_s) build_heads(pl, select);
+        for (Op& op : ops) if (op.kind == Op::ROWDOT) pl.flops += op.flops;
+
+        link_pdl(pl);
+        // One eager pass first: opts kernels into their shared-memory sizes and surfaces launch-configuration
+        // errors with a real message (errors inside a capture only invalidate the capture).
+        if (!ops.empty()) {
+            cudaStream_t ws;
+            CUDA_CHECK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+            try { run_ops(pl, ws); } catch (...) { cudaStreamSynchronize(ws); cudaStreamDestroy(ws); throw; }
+            cudaError_t e = cudaStreamSynchronize(ws);
+            cudaStreamDestroy(ws);
+            CUDA_CHECK(e);
+            if (opt.use_cuda_graph) capture(pl);
+        }
+        Plan* raw = up.get();
+        raw->last_use = ++use_clock;
+        plans[key] = std::move(up);
+        evict_plans(raw);
+        return raw;
+    }
+
+    // Plan cache bound (a MicroBatchWorker produces many (batch, length, regions) combinations): beyond max_plans the least
+    // recently used plan -- its workspace (about 1 MB per pair) and CUDA graph -- is destroyed.  Rare, so the device is drained
+    // first: a plan may still be executing on some stream.
+    void evict_plans(const Plan* keep) {
+        while (plans.size() > max_plans) {
+            auto victim = plans.end();
+            for (auto it = plans.begin(); it != plans.end(); ++it)
+                if (it->second.get() != keep && (victim == plans.end() || it->second->last_use < victim->second->last_use)) victim = it;
+            if (victim == plans.end()) break;
+            cudaDeviceSynchronize();
+            plans.erase(victim);
+        }
+    }
+
+    // ---- poolers + heads (main stream, after joining the image branch)
+    void build_heads(Plan& pl, uint32_t select) {
+        const Config& c = cfg;
+        const int B = pl.B, T = pl.T, V = pl.V, tc = pl.t_cur, vc = pl.v_cur;
+        const int Mt = B * T, Mv = B * V, H = c.hidden, Hv = c.v_hidden, Hb = c.bi_hidden;
+        const size_t S = x3 ? 3 : 1;
+        auto& ops = pl.ops;
         float* pooled_t = pl.mem.alloc_n<float>(static_cast<size_t>(B) * Hb);
         float* pooled = pl.mem.alloc_n<float>(static_cast<size_t>(B) * Hb);
-        bf16* pooled_b = pl.mem.alloc_n<bf16>(static_cast<size_t>(B) * Hb);
+        bf16* pooled_b = pl.mem.alloc_n<bf16>(static_cast<size_t>(B) * Hb * S);
         {
             add_linear(pl, pl.t_b16[tc], B, static_cast<int64_t>(T) * H, t_pool, vb::kActRelu, nullptr, 0, nullptr, nullptr, 0, pooled_t, Hb, 0, Op::JOIN);
             add_linear(pl, pl.v_b16[vc], B, static_cast<int64_t>(V) * Hv, v_pool, vb::kActRelu, nullptr, 0, nullptr, pooled_b, Hb, pooled, Hb, 0, Op::NONE, pooled_t, Hb);
         }
         pl.outs[11] = OutBuf{pooled, B, Hb, Hb};
-        pl.outs[9] = OutBuf{pl.t_f32[tc], Mt, H, H};
-        pl.outs[10] = OutBuf{pl.v_f32[vc], Mv, Hv, Hv};
         auto cls_head = [&](const ClsW& w, int n_out, int slot) {
-            bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(B) * 2 * Hb);
+            bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(B) * 2 * Hb * S);
             add_linear(pl, pooled_b, B, Hb, w.fc0, vb::kActGelu, nullptr, 0, &w.ln, hid, 2 * Hb, nullptr, 0);
             pl.outs[slot] = make_out(pl, B, n_out);
             add_linear(pl, hid, B, 2 * Hb, w.fc3, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[slot].p, pl.outs[slot].ld);
@@ -876,7 +1009,7 @@ struct vb200_engine {
             ops.push_back(rowdot_op(pooled, Hb, vil_tri, nullptr, pl.outs[4].p, pl.outs[4].ld, B));
         }
         if (select & VB200_OUT_VISION_PREDICTION) {
-            bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * Hv);
+            bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mv) * Hv * S);
             add_linear(pl, pl.v_b16[vc], Mv, Hv, img_transform, vb::kActGelu, nullptr, 0, &img_ln, hid, Hv, nullptr, 0);
             pl.outs[5] = make_out(pl, Mv, c.v_target);
             add_linear(pl, hid, Mv, Hv, img_decoder, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[5].p, pl.outs[5].ld);
@@ -886,7 +1019,7 @@ struct vb200_engine {
             ops.push_back(rowdot_op(pl.v_f32[vc], Hv, vision_logit, pl.mask_v, pl.outs[6].p, pl.outs[6].ld, Mv));
         }
         if (select & VB200_OUT_LINGUISIC_PREDICTION) {
-            bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * H);
+            bf16* hid = pl.mem.alloc_n<bf16>(static_cast<size_t>(Mt) * H * S);
             add_linear(pl, pl.t_b16[tc], Mt, H, lm_transform, vb::kActGelu, nullptr, 0, &lm_ln, hid, H, nullptr, 0);
             pl.outs[7] = make_out(pl, Mt, c.vocab);
             add_linear(pl, hid, Mt, H, lm_decoder, vb::kActNone, nullptr, 0, nullptr, nullptr, 0, pl.outs[7].p, pl.outs[7].ld);
@@ -895,32 +1028,13 @@ struct vb200_engine {
             pl.outs[8] = make_out(pl, Mt, 1);
             ops.push_back(rowdot_op(pl.t_f32[tc], H, ling_logit, nullptr, pl.outs[8].p, pl.outs[8].ld, Mt));
         }
-        for (Op& op : ops) if (op.kind == Op::ROWDOT) pl.flops += op.flops;
-
-        link_prefetch(pl);
-        link_pdl(pl);
-        // One eager pass first: opts kernels into their shared-memory sizes and surfaces launch-configuration
-        // errors with a real message (errors inside a capture only invalidate the capture).
-        {
-            cudaStream_t ws;
-            CUDA_CHECK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
-            try { run_ops(pl, ws); } catch (...) { cudaStreamSynchronize(ws); cudaStreamDestroy(ws); throw; }
-            cudaError_t e = cudaStreamSynchronize(ws);
-            cudaStreamDestroy(ws);
-            CUDA_CHECK(e);
-        }
-        if (opt.use_cuda_graph) capture(pl);
-        Plan* raw = up.get();
-        plans[key] = std::move(up);
-        return raw;
     }
 
     // ---------------------------------------------------------------- execution
     void launch_op(const Op& op, cudaStream_t st) {
         switch (op.kind) {
             case Op::GEMM:
-                if (gemm_v1) CUDA_CHECK(vb::launch_gemm(op.ta, op.tb, op.ep, op.block_n, op.ln, st));
-                else if (op.pair) CUDA_CHECK(vb::launch_gemm_pair(op.ta, op.tb, op.ep, op.block_n, st));
+                if (op.pair) CUDA_CHECK(vb::launch_gemm_pair(op.ta, op.tb, op.ep, op.block_n, st));
                 else {
                     GemmEpilogue e = op.ep;
                     e.tmap_c_host = e.tma_store ? &op.tc : nullptr;       // Op objects move when the list grows: bind here
@@ -937,9 +1051,14 @@ struct vb200_engine {
                                                    light_pdl(), opt.act_fp16, st));
                 break;
             case Op::LAYERNORM:
-                CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.n_out > 1 ? op.n_out : 1, static_cast<long long>(op.ln_M) * op.ln_N,
-                                                  op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
-                                                  op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, light_pdl(), st));
+                CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
+                                                  op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, x3 ? 1 : 0,
+                                                  light_pdl(), st));
+                break;
+            case Op::ATTN_F32:
+                CUDA_CHECK(vb::launch_attention_f32(op.f_q, op.f_ld_q, op.f_k, op.f_v, op.f_ld_kv, op.f_in, op.f_mask, op.B, op.f_Lq,
+                                                    op.f_Lk, op.heads, op.head_dim, op.f_ctx, op.f_ld_ctx, op.f_ctx_mode, op.f_probs,
+                                                    light_pdl(), st));
                 break;
             case Op::ROWDOT:
                 CUDA_CHECK(vb::launch_rowdot(op.x, op.ld_x, op.W, op.bias, op.add, op.out, op.ld_out, op.M, op.K, op.n_out, opt.use_pdl, st));
@@ -1025,30 +1144,11 @@ struct vb200_engine {
             const int st = op.stream & 1;
             if (op.kind == Op::GEMM && op.ep.pdl == 2 &&
                 (prev_kind[st] == Op::LAYERNORM || prev_kind[st] == Op::SELF_ATTN || prev_kind[st] == Op::CO_ATTN ||
+                 prev_kind[st] == Op::ATTN_F32 ||
                  (pdl_gemm_gemm && prev_kind[st] == Op::GEMM)))
                 op.ep.pdl = early_w ? 5 : 1;
             prev_kind[st] = op.kind;
             if (op.sync != Op::NONE) prev_kind[0] = prev_kind[1] = -1;      // fork / join: the predecessor set is not one kernel
-        }
-    }
-
-    // Every GEMM pulls the weights of the next GEMM of its graph branch into L2 while its own main loop runs (GemmEpilogue::
-    // prefetch).  The last GEMM of a branch prefetches the first weights of the step (the next batch starts there).
-    void link_prefetch(Plan& pl) {
-        if (!weight_prefetch) return;
-        const int n = static_cast<int>(pl.ops.size());
-        for (int i = 0; i < n; ++i) {
-            Op& a = pl.ops[i];
-            if (a.kind != Op::GEMM) continue;
-            int next = -1, any = -1;
-            for (int j = i + 1; j < n && next < 0; ++j) {
-                if (pl.ops[j].kind != Op::GEMM) continue;
-                if (any < 0) any = j;
-                if (pl.ops[j].stream == a.stream) next = j;
-            }
-            if (next < 0) next = any;
-            if (next < 0) for (int j = 0; j < i && next < 0; ++j) if (pl.ops[j].kind == Op::GEMM) next = j;
-            if (next >= 0) { a.ep.prefetch = pl.ops[next].w; a.ep.prefetch_bytes = pl.ops[next].w_bytes; }
         }
     }
 
@@ -1079,10 +1179,66 @@ struct vb200_engine {
             fail(VB200_ERR_INVALID, "vb200_inputs has a NULL required pointer");
         CUDA_CHECK(vb::launch_text_embed(in.question, in.segment_ids, in.input_mask, in.task_tokens, word, pos, type, task,
                                          emb_ln.g, emb_ln.b, c.ln_eps, pl.t_f32[0], pl.t_b16[0], pl.mask_t, pl.B, pl.Tin,
-                                         c.hidden, c.vocab, c.max_pos, c.type_vocab, c.n_task, c.task_tokens, opt.act_fp16, st));
-        CUDA_CHECK(vb::launch_image_pack(in.features, in.spatials, in.image_mask, pl.img_a, pl.mask_v, pl.B * pl.V, c.v_feat, pl.kp, opt.act_fp16, st));
+                                         c.hidden, c.vocab, c.max_pos, c.type_vocab, c.n_task, c.task_tokens, opt.act_fp16, x3 ? 1 : 0, st));
+        CUDA_CHECK(vb::launch_image_pack(in.features, in.spatials, in.image_mask, pl.img_a, pl.mask_v, pl.B * pl.V, c.v_feat, pl.kp,
+                                         opt.act_fp16, x3 ? 1 : 0, st));
+        run_plan(pl, st);
+    }
+    void run_plan(Plan& pl, cudaStream_t st) {
+        if (pl.ops.empty()) return;
         if (pl.exec) CUDA_CHECK(cudaGraphLaunch(pl.exec, st));
         else run_ops(pl, st);
+    }
+    // worker.py:422-455 on the device: detector output -> operand rows / masks, then the same plan as forward_device
+    void forward_regions(Plan& pl, const vb200_region_inputs& in, cudaStream_t st) {
+        const Config& c = cfg;
+        if (!in.question || !in.segment_ids || !in.input_mask || (c.task_tokens && !in.task_tokens) || !in.box_features || !in.boxes ||
+            !in.image_wh)
+            fail(VB200_ERR_INVALID, "vb200_region_inputs has a NULL required pointer");
+        CUDA_CHECK(vb::launch_text_embed(in.question, in.segment_ids, in.input_mask, in.task_tokens, word, pos, type, task,
+                                         emb_ln.g, emb_ln.b, c.ln_eps, pl.t_f32[0], pl.t_b16[0], pl.mask_t, pl.B, pl.Tin,
+                                         c.hidden, c.vocab, c.max_pos, c.type_vocab, c.n_task, c.task_tokens, opt.act_fp16, x3 ? 1 : 0, st));
+        CUDA_CHECK(vb::launch_region_pack(in.box_features, in.boxes, in.image_wh, in.num_boxes, pl.img_a, pl.mask_v, in.spatials_out,
+                                          pl.B, pl.V - 1, c.v_feat, pl.kp, opt.act_fp16, x3 ? 1 : 0, st));
+        run_plan(pl, st);
+    }
+    // ---- retrieval reuse (PlanMode): per-caption / per-image prefixes and the pair suffix
+    void encode_text(int n, int Tin, const int64_t* q, const int64_t* seg, const int64_t* im, const int64_t* tk, float* st_f32,
+                     void* st_16, float* st_mask, cudaStream_t st) {
+        const Config& c = cfg;
+        if (!q || !seg || !im || (c.task_tokens && !tk) || !st_f32 || !st_16 || !st_mask) fail(VB200_ERR_INVALID, "vb200_encode_text: NULL pointer");
+        Plan& pl = *get_plan(n, Tin, 1, 0, 0, TEXT_PREFIX);
+        CUDA_CHECK(vb::launch_text_embed(q, seg, im, tk, word, pos, type, task, emb_ln.g, emb_ln.b, c.ln_eps, pl.t_f32[0], pl.t_b16[0],
+                                         pl.mask_t, pl.B, pl.Tin, c.hidden, c.vocab, c.max_pos, c.type_vocab, c.n_task, c.task_tokens,
+                                         opt.act_fp16, x3 ? 1 : 0, st));
+        run_plan(pl, st);
+        const size_t rows = static_cast<size_t>(pl.B) * pl.T, S = x3 ? 3 : 1;
+        CUDA_CHECK(cudaMemcpyAsync(st_f32, pl.t_f32[pl.t_cur], rows * c.hidden * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(st_16, pl.t_b16[pl.t_cur], rows * c.hidden * S * 2, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(st_mask, pl.mask_t, rows * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    void encode_image(int n, int V, const float* feats, const float* loc, const uint8_t* vmask, float* st_f32, void* st_16,
+                      float* st_mask, cudaStream_t st) {
+        const Config& c = cfg;
+        if (!feats || !loc || !vmask || !st_f32 || !st_16 || !st_mask) fail(VB200_ERR_INVALID, "vb200_encode_image: NULL pointer");
+        Plan& pl = *get_plan(n, 1, V, 0, 0, IMAGE_PREFIX);
+        CUDA_CHECK(vb::launch_image_pack(feats, loc, vmask, pl.img_a, pl.mask_v, pl.B * pl.V, c.v_feat, pl.kp, opt.act_fp16, x3 ? 1 : 0, st));
+        run_plan(pl, st);
+        const size_t rows = static_cast<size_t>(pl.B) * pl.V, S = x3 ? 3 : 1;
+        CUDA_CHECK(cudaMemcpyAsync(st_f32, pl.v_f32[pl.v_cur], rows * c.v_hidden * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(st_16, pl.v_b16[pl.v_cur], rows * c.v_hidden * S * 2, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(st_mask, pl.mask_v, rows * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    void forward_cached(Plan& pl, const int32_t* t_idx, int n_text, const float* t_f32, const void* t_16, const float* t_mask,
+                        const int32_t* v_idx, int n_img, const float* v_f32, const void* v_16, const float* v_mask, cudaStream_t st) {
+        const Config& c = cfg;
+        if (!t_idx || !t_f32 || !t_16 || !t_mask || !v_idx || !v_f32 || !v_16 || !v_mask) fail(VB200_ERR_INVALID, "vb200_forward_cached: NULL pointer");
+        const int S = x3 ? 3 : 1;
+        CUDA_CHECK(vb::launch_gather_state(t_idx, n_text, t_f32, t_16, t_mask, pl.t_f32[0], pl.t_b16[0], pl.mask_t, pl.B, pl.T,
+                                           c.hidden, c.hidden * S, st));
+        CUDA_CHECK(vb::launch_gather_state(v_idx, n_img, v_f32, v_16, v_mask, pl.v_f32[0], pl.v_b16[0], pl.mask_v, pl.B, pl.V,
+                                           c.v_hidden, c.v_hidden * S, st));
+        run_plan(pl, st);
     }
     static float* out_ptr(const vb200_outputs& o, int slot) {
         switch (slot) {
@@ -1101,6 +1257,15 @@ struct vb200_engine {
             if (o.p == nullptr) fail(VB200_ERR_INVALID, "output slot %d requested but not selected in the `select` mask", s);
             CUDA_CHECK(cudaMemcpy2DAsync(dst, static_cast<size_t>(o.cols) * 4, o.p, static_cast<size_t>(o.ld) * 4,
                                          static_cast<size_t>(o.cols) * 4, o.rows, kind, st));
+        }
+        if (out.attention_probs != nullptr) {
+            if (pl.attn.empty()) fail(VB200_ERR_INVALID, "attention_probs requested but VB200_OUT_ATTENTION is not set in `select`");
+            float* dst = out.attention_probs;
+            for (const Plan::AttnOut& a : pl.attn) {
+                const size_t n = static_cast<size_t>(pl.B) * a.heads * a.Lq * a.Lk;
+                CUDA_CHECK(cudaMemcpyAsync(dst, a.p, n * 4, kind, st));
+                dst += n;
+            }
         }
     }
 };
@@ -1153,22 +1318,24 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         o.strict = o.strict >= 0 ? 1 : 0;
         const int pdl_req = o.use_pdl;
         o.use_pdl = o.use_pdl > 0 ? 1 : 0;
-        o.act_fp16 = o.act_fp16 >= 0 ? 1 : 0;
-        o.fused_layernorm = o.fused_layernorm > 0 ? 1 : 0;
+        o.split_fp32 = o.split_fp32 > 0 ? 1 : 0;
+        o.act_fp16 = (o.act_fp16 >= 0 || o.split_fp32) ? 1 : 0;
+        o.fused_layernorm = (o.fused_layernorm > 0 && !o.split_fp32) ? 1 : 0;
         Config c = parse_config(config_json);
         {   // audit the state_dict (names, shapes, dtypes, strictness) before touching any device
             vb200_engine audit;
-            audit.cfg = c; audit.opt = o; audit.dry = true;
+            audit.cfg = c; audit.opt = o; audit.dry = true; audit.x3 = o.split_fp32 != 0;
             audit.ingest(n_tensors, tensors);
         }
         require_device(o.device);
         eng = new vb200_engine();
         eng->cfg = c;
         eng->opt = o;
-        if (const char* v = getenv("VB200_GEMM")) eng->gemm_v1 = (strcmp(v, "v1") == 0);
+        eng->x3 = o.split_fp32 != 0;
         eng->fused_ln = o.fused_layernorm != 0;
-        if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0);
-        if (const char* v = getenv("VB200_SPLITK")) { eng->split_k_enabled = (strcmp(v, "1") == 0); eng->split_k_fixed = (strcmp(v, "2") == 0); }
+        if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
+        eng->max_plans = o.max_plans > 0 ? static_cast<size_t>(o.max_plans) : 24;
+        if (const char* v = getenv("VB200_MAX_PLANS")) { const int n = atoi(v); if (n > 0) eng->max_plans = static_cast<size_t>(n); }
         eng->pdl_light = eng->pdl_medium = false;
         if (pdl_req == 0) eng->opt.use_pdl = 1;               // default: full
         if (const char* v = getenv("VB200_PDL")) {
@@ -1180,7 +1347,6 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         }
         if (const char* v = getenv("VB200_TMASTORE")) eng->tma_store_enabled = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_EARLYW")) eng->early_w = (strcmp(v, "0") != 0);
-        if (const char* v = getenv("VB200_PREFETCH")) eng->weight_prefetch = (strcmp(v, "1") == 0);
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
@@ -1213,10 +1379,92 @@ int vb200_forward_slot(vb200_handle h, const vb200_inputs* in, const vb200_outpu
     return guard(h, [&] {
         if (in == nullptr || out == nullptr) fail(VB200_ERR_INVALID, "inputs/outputs struct is NULL");
         CUDA_CHECK(cudaSetDevice(h->opt.device));
-        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL, slot);
+        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL, slot, vb200_engine::FULL,
+                               (select & VB200_OUT_ATTENTION) != 0);
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
         h->forward_device(*pl, *in, st);
         h->copy_outputs(*pl, *out, st, cudaMemcpyDeviceToDevice);
+    });
+}
+
+int vb200_forward_regions(vb200_handle h, const vb200_region_inputs* in, const vb200_outputs* out, uint32_t select, int32_t slot,
+                          void* cuda_stream) {
+    if (h == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        if (in == nullptr || out == nullptr) fail(VB200_ERR_INVALID, "inputs/outputs struct is NULL");
+        if (in->n_boxes < 1) fail(VB200_ERR_INVALID, "n_boxes must be positive");
+        CUDA_CHECK(cudaSetDevice(h->opt.device));
+        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_boxes + 1, select & VB200_OUT_ALL, slot, vb200_engine::FULL,
+                               (select & VB200_OUT_ATTENTION) != 0);
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        h->forward_regions(*pl, *in, st);
+        h->copy_outputs(*pl, *out, st, cudaMemcpyDeviceToDevice);
+    });
+}
+
+int vb200_encode_text(vb200_handle h, int32_t n, int32_t n_tokens, const int64_t* question, const int64_t* segment_ids,
+                      const int64_t* input_mask, const int64_t* task_tokens, float* state_f32, void* state_16, float* state_mask,
+                      void* cuda_stream) {
+    if (h == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        CUDA_CHECK(cudaSetDevice(h->opt.device));
+        h->encode_text(n, n_tokens, question, segment_ids, input_mask, task_tokens, state_f32, state_16, state_mask,
+                       static_cast<cudaStream_t>(cuda_stream));
+    });
+}
+
+int vb200_encode_image(vb200_handle h, int32_t n, int32_t n_regions, const float* features, const float* spatials,
+                       const uint8_t* image_mask, float* state_f32, void* state_16, float* state_mask, void* cuda_stream) {
+    if (h == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        CUDA_CHECK(cudaSetDevice(h->opt.device));
+        h->encode_image(n, n_regions, features, spatials, image_mask, state_f32, state_16, state_mask,
+                        static_cast<cudaStream_t>(cuda_stream));
+    });
+}
+
+int vb200_forward_cached(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, const int32_t* text_index,
+                         int32_t n_text, const float* text_f32, const void* text_16, const float* text_mask,
+                         const int32_t* image_index, int32_t n_image, const float* image_f32, const void* image_16,
+                         const float* image_mask, const vb200_outputs* out, uint32_t select, int32_t slot, void* cuda_stream) {
+    if (h == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        if (out == nullptr) fail(VB200_ERR_INVALID, "outputs struct is NULL");
+        if (n_text < 1 || n_image < 1) fail(VB200_ERR_INVALID, "cached state counts must be positive");
+        CUDA_CHECK(cudaSetDevice(h->opt.device));
+        Plan* pl = h->get_plan(batch, n_tokens, n_regions, select & VB200_OUT_ALL, slot, vb200_engine::SUFFIX,
+                               (select & VB200_OUT_ATTENTION) != 0);
+        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+        h->forward_cached(*pl, text_index, n_text, text_f32, text_16, text_mask, image_index, n_image, image_f32, image_16,
+                          image_mask, st);
+        h->copy_outputs(*pl, *out, st, cudaMemcpyDeviceToDevice);
+    });
+}
+
+int vb200_attention_layout(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, int32_t max_entries,
+                           int32_t* n_entries, int32_t* dims, int64_t* offsets, int64_t* total_floats) {
+    if (h == nullptr || n_entries == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        // derived from the layer schedule alone (no plan is built): the order add_attn_f32 is called in by get_plan
+        const Config& c = h->cfg;
+        const int T = n_tokens + (c.task_tokens ? 1 : 0), V = n_regions;
+        int n = 0;
+        int64_t off = 0;
+        auto put = [&](int heads, int lq, int lk, int kind) {
+            if (n < max_entries) {
+                if (dims) { dims[4 * n] = heads; dims[4 * n + 1] = lq; dims[4 * n + 2] = lk; dims[4 * n + 3] = kind; }
+                if (offsets) offsets[n] = off;
+            }
+            off += static_cast<int64_t>(batch) * heads * lq * lk;
+            ++n;
+        };
+        for (const std::string& step : h->schedule) {
+            if (step[0] == 'T') put(c.heads, T, T, 0);
+            else if (step[0] == 'V') put(c.v_heads, V, V, 1);
+            else { put(c.bi_heads, T, V, 2); put(c.bi_heads, V, T, 3); }
+        }
+        *n_entries = n;
+        if (total_floats) *total_floats = off;
     });
 }
 
@@ -1230,7 +1478,8 @@ int vb200_forward_host_slot(vb200_handle h, const vb200_inputs* in, const vb200_
     return guard(h, [&] {
         if (in == nullptr || out == nullptr) fail(VB200_ERR_INVALID, "inputs/outputs struct is NULL");
         CUDA_CHECK(cudaSetDevice(h->opt.device));
-        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL, slot);
+        Plan* pl = h->get_plan(in->batch, in->n_tokens, in->n_regions, select & VB200_OUT_ALL, slot, vb200_engine::FULL,
+                               (select & VB200_OUT_ATTENTION) != 0);
         cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
         const size_t B = pl->B, Tin = pl->Tin, V = pl->V, F = h->cfg.v_feat;
         if (pl->d_q == nullptr) {
@@ -1305,6 +1554,9 @@ int vb200_model_dim(vb200_handle h, const char* key, int64_t* value) {
         else if (k == "num_labels") *value = h->num_labels; else if (k == "gqa_labels") *value = h->gqa_labels;
         else if (k == "task_specific_tokens") *value = c.task_tokens;
         else if (k == "weight_bytes") *value = static_cast<int64_t>(h->weights.total);
+        else if (k == "operand_width_factor") *value = h->x3 ? 3 : 1;
+        else if (k == "n_plans") *value = static_cast<int64_t>(h->plans.size());
+        else if (k == "n_layers_scheduled") *value = static_cast<int64_t>(h->schedule.size());
         else fail(VB200_ERR_INVALID, "unknown model dimension \"%s\"", key);
     });
 }
@@ -1324,9 +1576,8 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
     return op_guard([&] {
         const bool ln = gamma != nullptr;
         const bool pair = variant == 2;                                    // CTA-pair kernel: block_n 128 (default) or 256
-        int bn = block_n > 0 ? block_n
-                             : (pair ? 128 : variant == 1 ? vb::gemm_pick_block_n(static_cast<int>(N), ln)
-                                                          : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
+        if (variant != 0 && variant != 2) fail(VB200_ERR_INVALID, "vb200_linear: variant %d does not exist (0 persistent, 2 CTA pair)", variant);
+        int bn = block_n > 0 ? block_n : (pair ? 128 : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
         if (bn == 0) fail(VB200_ERR_INVALID, "no tiling for N=%lld with LayerNorm", (long long)N);
         CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128, act_fp16 != 0);
         CUtensorMap tb = make_tmap(w_bf16, N, K, ld_w, pair ? bn / 2 : bn, act_fp16 != 0);
@@ -1335,11 +1586,11 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
         e.gamma = gamma; e.beta = beta; e.eps = eps; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = (int)ld_y_bf16;
         e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.pdl = use_pdl;
         e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16; e.timing = timing;
+        if (const char* dbg = getenv("VB200_DEBUG")) e.debug = atoi(dbg);          // timing decomposition (kernels.h), op entry only
         CUtensorMap tc;
         const char* ts = getenv("VB200_TMASTORE");
         if (variant == 0 && !ln && !(ts && strcmp(ts, "0") == 0)) { setup_tma_store(&tc, e); e.tmap_c_host = e.tma_store ? &tc : nullptr; }
-        if (variant == 1) CUDA_CHECK(vb::launch_gemm(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
-        else if (pair) CUDA_CHECK(vb::launch_gemm_pair(ta, tb, e, bn, static_cast<cudaStream_t>(cuda_stream)));
+        if (pair) CUDA_CHECK(vb::launch_gemm_pair(ta, tb, e, bn, static_cast<cudaStream_t>(cuda_stream)));
         else CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
     });
 }
@@ -1348,9 +1599,43 @@ int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t
                     float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
                     int32_t act_fp16, void* cuda_stream) {
     return op_guard([&] {
-        CUDA_CHECK(vb::launch_ln_residual(y, (int)ld_y, 1, 0, residual, (int)ld_res, gamma, beta, eps, out_f32, (int)ld_f32,
-                                          static_cast<bf16*>(out_16), (int)ld_16, (int)M, (int)N, act_fp16 ? 1 : 0, 0,
+        CUDA_CHECK(vb::launch_ln_residual(y, (int)ld_y, residual, (int)ld_res, gamma, beta, eps, out_f32, (int)ld_f32,
+                                          static_cast<bf16*>(out_16), (int)ld_16, (int)M, (int)N, act_fp16 ? 1 : 0, 0, 0,
                                           static_cast<cudaStream_t>(cuda_stream)));
+    });
+}
+
+int vb200_layernorm_split(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
+                          float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N, void* cuda_stream) {
+    return op_guard([&] {
+        CUDA_CHECK(vb::launch_ln_residual(y, (int)ld_y, residual, (int)ld_res, gamma, beta, eps, out_f32, (int)ld_f32,
+                                          static_cast<bf16*>(out_16), (int)ld_16, (int)M, (int)N, 1, 1, 0,
+                                          static_cast<cudaStream_t>(cuda_stream)));
+    });
+}
+
+int vb200_linear_split(const void* x16, int64_t ld_x, const void* w16, int64_t ld_w, const float* bias, int32_t act, void* y16,
+                       int64_t ld_y16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K3, void* cuda_stream) {
+    return op_guard([&] {
+        if (K3 % 192 != 0) fail(VB200_ERR_INVALID, "vb200_linear_split: K3 = %lld is not 3 x a multiple of 64", (long long)K3);
+        const int bn = vb::gemm_p_pick_block_n(static_cast<int>(N), false);
+        CUtensorMap ta = make_tmap(x16, M, K3, ld_x, 128, true);
+        CUtensorMap tb = make_tmap(w16, N, K3, ld_w, bn, true);
+        GemmEpilogue e{};
+        e.M = (int)M; e.N = (int)N; e.K = (int)K3; e.bias = bias; e.eps = 0.0f; e.out_bf16 = static_cast<bf16*>(y16);
+        e.ld_bf16 = (int)ld_y16; e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.a_f16 = 1; e.out_f16 = 1;
+        e.split16 = y16 != nullptr ? 1 : 0;
+        CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, false, static_cast<cudaStream_t>(cuda_stream)));
+    });
+}
+
+int vb200_attention_f32(const void* q, int64_t ld_q, const void* k, const void* v, int64_t ld_kv, int32_t in_kind,
+                        const float* key_mask_add, int32_t B, int32_t Lq, int32_t Lk, int32_t heads, int32_t head_dim, void* ctx,
+                        int64_t ld_ctx, int32_t ctx_mode, float* probs, void* cuda_stream) {
+    return op_guard([&] {
+        CUDA_CHECK(vb::launch_attention_f32(q, (int)ld_q, k, v, (int)ld_kv, in_kind, key_mask_add, B, Lq, Lk, heads, head_dim,
+                                            static_cast<bf16*>(ctx), (int)ld_ctx, ctx_mode, probs, 0,
+                                            static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 

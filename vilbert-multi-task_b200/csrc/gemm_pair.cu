@@ -220,12 +220,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int et = threadIdx.x - 64;
         const bool st_fast = (p.out_bf16 == nullptr || (p.ld_bf16 & 7) == 0) && (p.out_f32 == nullptr || (p.ld_f32 & 3) == 0);
         const uint32_t leader_empty0 = mapa_u32(&tmem_empty_bar[0], 0);
-        if (p.prefetch != nullptr) {                     // next GEMM's weights -> L2 (see gemm_persistent.cuh)
-            const long long lines = (p.prefetch_bytes + 127) >> 7;
-            const long long nthr = static_cast<long long>(gridDim.x) * kEpiThreads;
-            for (long long l = static_cast<long long>(blockIdx.x) * kEpiThreads + et; l < lines; l += nthr)
-                prefetch_l2(static_cast<const uint8_t*>(p.prefetch) + (l << 7));
-        }
         uint32_t it = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
             const uint32_t acc = Cfg::kAccBufs == 2 ? (it & 1u) : 0u;
@@ -395,7 +389,7 @@ int num_sms_host() { return pgemm::num_sms(); }
 // tb must have been built with box rows = block_n / 2 (each CTA of a pair loads half of the tile's W rows)
 cudaError_t launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int block_n, cudaStream_t st) {
     if (ep.M < 1 || ep.N < 1 || ep.K < 1 || ep.N % block_n != 0 || ep.res != nullptr || ep.gamma != nullptr ||
-        ep.a_f16 != ep.out_f16 || ep.split_k > 1)
+        ep.a_f16 != ep.out_f16 || ep.split16 || ep.act == kActGeluExact)
         return cudaErrorInvalidValue;
     switch (block_n) {
         case 128: return pgemm::dispatch_pair<128>(ta, tb, ep, st);

@@ -4,7 +4,7 @@
 
 namespace vb {
 
-enum Act : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+enum Act : int { kActNone = 0, kActGelu = 1, kActRelu = 2, kActGeluExact = 3 };   // 3: erf to 1.5e-7 (fp32-parity mode)
 
 // Epilogue of the tcgen05 GEMM:  x = act(acc + bias + res) * mul ; LN variant: y = LayerNorm(x) * gamma + beta.
 struct GemmEpilogue {
@@ -29,19 +29,15 @@ struct GemmEpilogue {
                                   // griddepcontrol.wait (weights do not depend on the previous kernel)
     int a_f16;                    // both GEMM operands (activations A, weights W) are fp16 instead of bf16
     int out_f16;                  // 16-bit output is fp16 instead of bf16
-    int split_k;                  // plain kernel only: K is cut into split_k slices, slice s writes its fp32 partial sum to
-    long long split_stride;       //   out_f32 + s * split_stride (bias added by slice 0); the row LayerNorm kernel sums them
+    int split16;                  // fp32-parity mode: the 16-bit output is written as fp16 hi | lo | hi per 64 columns
+                                  // (common.cuh split_col; ld_bf16 is the stride of that 3x wider buffer); plain kernel only
     long long* timing;            // optional (profiling): 8 clock64 stamps per CTA, see gemm_persistent.cu; null in production
     const void* tmap_c_host;      // host pointer to the CUtensorMap of the output (launchers copy it into a kernel parameter)
     int tma_store;                // 0: register/LSU stores only; 1: 16-bit output, 2: fp32 output may leave through a TMA store
                                   // (plain persistent kernel: the LAST tile of every CTA is staged in the idle operand ring)
-    const void* prefetch;         // optional: the NEXT GEMM's weight matrix; the (otherwise idle) epilogue warps pull it into L2
-    long long prefetch_bytes;     //   while this kernel's main loop runs -- a step touches 466 MB of weights, so without this
+    int debug;                    // timing decomposition only (VB200_DEBUG through vb200_linear): 1 = issue no MMA, 2 = no epilogue
+                                  // stores, 4 = no operand loads (the ring is "filled" by plain arrives); results are garbage
 };                                //   every GEMM starts on HBM misses (weights never survive in the 126 MB L2 until the next step)
-
-int gemm_pick_block_n(int N, bool ln);
-cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep, int block_n,
-                        bool ln, cudaStream_t st);
 
 // v2: persistent CTAs / clusters, TMEM double-buffered accumulators, single-exchange LayerNorm (gemm_persistent.cu)
 int gemm_p_pick_block_n(int N, bool ln);
@@ -67,19 +63,32 @@ cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const 
                                 __nv_bfloat16* ctx_txt, int ld_ctx_txt, __nv_bfloat16* ctx_img, int ld_ctx_img, int B,
                                 int T, int V, int heads, int head_dim, int pdl, int f16, cudaStream_t st);
 
-// un-fused LayerNorm(y + res): fp32 stream out + 16-bit operand out (layernorm.cu)
-cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long long partial_stride, const float* res, int ld_res,
-                               const float* gamma, const float* beta, float eps, float* out_f32, int ld_f32,
-                               __nv_bfloat16* out16, int ld16, int M, int N, int f16, int pdl, cudaStream_t st);
+// un-fused LayerNorm(y + res): fp32 stream out + 16-bit operand out (layernorm.cu); split16: hi | lo | hi operand (fp32-parity mode)
+cudaError_t launch_ln_residual(const float* y, int ld_y, const float* res, int ld_res, const float* gamma, const float* beta,
+                               float eps, float* out_f32, int ld_f32, __nv_bfloat16* out16, int ld16, int M, int N, int f16,
+                               int split16, int pdl, cudaStream_t st);
 // K2: word + position + token-type gather, task-token row at index 1, LayerNorm; also builds the additive text mask.
 cudaError_t launch_text_embed(const int64_t* ids, const int64_t* seg, const int64_t* input_mask, const int64_t* task,
                               const float* word, const float* pos, const float* type, const float* task_tab,
                               const float* gamma, const float* beta, float eps, float* out_f32,
                               __nv_bfloat16* out_bf16, float* mask_add, int B, int Tin, int H, int vocab, int max_pos,
-                              int n_type, int n_task, int task_tokens, int f16, cudaStream_t st);
+                              int n_type, int n_task, int task_tokens, int f16, int split16, cudaStream_t st);
 // K1 (input half): fp32 region features + 5-d boxes -> bf16 GEMM operand [B*V, Kp] = [feat | loc | 0], additive image mask.
 cudaError_t launch_image_pack(const float* feats, const float* loc, const uint8_t* image_mask, __nv_bfloat16* a_out,
-                              float* mask_add, int rows, int F, int Kp, int f16, cudaStream_t st);
+                              float* mask_add, int rows, int F, int Kp, int f16, int split16, cudaStream_t st);
+// custom_prediction()'s tensor construction on the device (worker.py:422-455): box features [B, n, F] + pixel boxes [B, n, 4] +
+// image sizes [B, 2] (+ optional valid-box counts) -> operand rows [B * (n + 1), Kp] with the global mean row first, masks, spatials.
+cudaError_t launch_region_pack(const float* box_feats, const float* boxes, const float* image_wh, const int32_t* num_boxes,
+                               __nv_bfloat16* a_out, float* mask_add, float* spatials_out, int B, int n, int F, int Kp, int f16,
+                               int split16, cudaStream_t st);
+// retrieval reuse: cached encoder state rows idx[b] -> sample b of a pair plan (fp32 stream [L, H], 16-bit operand [L, H16], mask [L])
+cudaError_t launch_gather_state(const int32_t* idx, int n_src, const float* src_f32, const void* src_16, const float* src_mask,
+                                float* dst_f32, void* dst_16, float* dst_mask, int B, int L, int H, int H16, cudaStream_t st);
+// fp32 CUDA-core attention (attention_f32.cu): in_kind 0 fp32 / 1 fp16 / 2 bf16 Q, K, V; ctx_mode 0 none / 1 fp16 / 2 bf16 /
+// 3 fp16 hi | lo | hi; probs: optional [B, heads, Lq, Lk] fp32 attention probabilities.
+cudaError_t launch_attention_f32(const void* q, int ld_q, const void* k, const void* v, int ld_kv, int in_kind,
+                                 const float* key_mask_add, int B, int Lq, int Lk, int heads, int D, __nv_bfloat16* ctx, int ld_ctx,
+                                 int ctx_mode, float* probs, int pdl, cudaStream_t st);
 // K8 (narrow heads): out[m, j] = dot(x[m, :K], W[j, :K]) + b[j] + (add ? add[m] : 0), j < n_out <= 4.
 cudaError_t launch_rowdot(const float* x, int ld_x, const float* W, const float* b, const float* add, float* out,
                           int ld_out, int M, int K, int n_out, int pdl, cudaStream_t st);

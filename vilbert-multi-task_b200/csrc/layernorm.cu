@@ -16,10 +16,10 @@ constexpr int kLnMaxVec = 16;   // N <= 2048: float4 per lane per 128 columns
 
 // NV = float4 vectors per lane (N / 128): 6 for the 768-wide text stream, 8 for 1024; kLnMaxVec covers everything up to 2048
 // with run-time predication (the specialised forms carry a third of the instructions and registers).
-template <bool F16, bool PARTIALS, int NV>
+// SPLIT: fp32-parity mode, the 16-bit output is written as fp16 hi | lo | hi per 64 columns (common.cuh split_col).
+template <bool F16, bool SPLIT, int NV>
 __global__ void __launch_bounds__(256)
-ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long long partial_stride,
-                   const float* __restrict__ res, int ld_res,
+ln_residual_kernel(const float* __restrict__ y, int ld_y, const float* __restrict__ res, int ld_res,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ out_f32, int ld_f32, uint16_t* __restrict__ out16, int ld16, int M, int N, int pdl) {
     if (pdl) pdl_wait();
@@ -35,10 +35,6 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
     for (int k = 0; k < NV; ++k) {
         if (k < nvec) {
             float4 a = yp[lane + 32 * k];
-            if (PARTIALS) for (int sp = 1; sp < n_partials; ++sp) {          // split-K partial sums of the producing GEMM
-                const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(yp + lane + 32 * k) + sp * partial_stride);
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
             if (rp) { const float4 r = rp[lane + 32 * k]; a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
             x[k] = a;
             s += a.x + a.y + a.z + a.w;
@@ -69,24 +65,35 @@ ln_residual_kernel(const float* __restrict__ y, int ld_y, int n_partials, long l
             o.z = (x[k].z - mean) * rstd * g.z + b.z;
             o.w = (x[k].w - mean) * rstd * g.w + b.w;
             if (of) of[lane + 32 * k] = o;
-            if (oh) oh[lane + 32 * k] = make_uint2(pack16x2<F16>(o.x, o.y), pack16x2<F16>(o.z, o.w));
+            if constexpr (SPLIT) {
+                if (oh) {
+                    const int c = 4 * (lane + 32 * k);                 // logical column of o.x; 4 columns stay inside one 64-group
+                    uint2* o3 = reinterpret_cast<uint2*>(out16 + static_cast<size_t>(row) * ld16 + split_col(c));
+                    const uint2 hi = make_uint2(pack16x2_rt(o.x, o.y, 1), pack16x2_rt(o.z, o.w, 1));
+                    o3[0] = hi;
+                    o3[16] = make_uint2(pack16x2_rt(split_lo(o.x), split_lo(o.y), 1), pack16x2_rt(split_lo(o.z), split_lo(o.w), 1));
+                    o3[32] = hi;
+                }
+            } else {
+                if (oh) oh[lane + 32 * k] = make_uint2(pack16x2<F16>(o.x, o.y), pack16x2<F16>(o.z, o.w));
+            }
         }
     }
 }
 
-cudaError_t launch_ln_residual(const float* y, int ld_y, int n_partials, long long partial_stride, const float* res, int ld_res,
-                               const float* gamma, const float* beta, float eps, float* out_f32, int ld_f32,
-                               __nv_bfloat16* out16, int ld16, int M, int N, int f16, int pdl, cudaStream_t st) {
+cudaError_t launch_ln_residual(const float* y, int ld_y, const float* res, int ld_res, const float* gamma, const float* beta,
+                               float eps, float* out_f32, int ld_f32, __nv_bfloat16* out16, int ld16, int M, int N, int f16,
+                               int split16, int pdl, cudaStream_t st) {
     if (N % 128 != 0 || N / 128 > kLnMaxVec || (ld_y & 3) || (res && (ld_res & 3)) || (out_f32 && (ld_f32 & 3)) ||
-        (out16 && (ld16 & 3)) || M < 1 || n_partials < 1 || (n_partials > 1 && (partial_stride & 3)))
+        (out16 && (ld16 & 3)) || M < 1 || (split16 && !f16))
         return cudaErrorInvalidValue;
     // one warp per row; 2 rows per CTA: 992 CTAs for 1984 rows spread 7:6 over the 148 SMs (8 rows per CTA: 248 CTAs, 2:1)
     static const int rows_per_cta = [] { const char* e = getenv("VB200_LN_ROWS"); const int v = e ? atoi(e) : 2; return (v >= 1 && v <= 8) ? v : 2; }();
     const dim3 grid((M + rows_per_cta - 1) / rows_per_cta), block(32 * rows_per_cta);
     uint16_t* o16 = reinterpret_cast<uint16_t*>(out16);
-#define VB_LN(F, P, V) launch_ex(ln_residual_kernel<F, P, V>, grid, block, 0, pdl, st, y, ld_y, n_partials, partial_stride, res, \
-                               ld_res, gamma, beta, eps, out_f32, ld_f32, o16, ld16, M, N, pdl)
-    if (n_partials > 1) return f16 ? VB_LN(true, true, kLnMaxVec) : VB_LN(false, true, kLnMaxVec);
+#define VB_LN(F, S, V) launch_ex(ln_residual_kernel<F, S, V>, grid, block, 0, pdl, st, y, ld_y, res, ld_res, gamma, beta, eps, \
+                               out_f32, ld_f32, o16, ld16, M, N, pdl)
+    if (split16) return VB_LN(true, true, kLnMaxVec);
     if (N == 768) return f16 ? VB_LN(true, false, 6) : VB_LN(false, false, 6);
     if (N == 1024) return f16 ? VB_LN(true, false, 8) : VB_LN(false, false, 8);
     return f16 ? VB_LN(true, false, kLnMaxVec) : VB_LN(false, false, kLnMaxVec);

@@ -30,6 +30,10 @@ from . import _lib as L
 # (the reference keeps `model`, `tokenizer`, `feature_extractor` as module globals, worker.py:464-466)
 model = None
 tokenizer = None
+# One engine handle serves one host thread at a time (plan cache and last_error are per handle, unlocked): every model call
+# of this module -- prediction(), prediction_batch(), the MicroBatchWorker thread -- takes this lock.
+import threading as _threading
+model_lock = _threading.RLock()
 label_maps: Dict[str, Optional[list]] = {"vqa": None, "gqa": None}
 
 MAX_LENGTH = 37                     # worker.py:408
@@ -138,19 +142,27 @@ def prediction(question, features, spatials, segment_ids, input_mask, image_mask
     _validate(task_id, infos)
     question, input_mask, segment_ids, task_tokens = _expand_text(task_id, features.size(0), question, input_mask,
                                                                   segment_ids, task_tokens)
-    out = model(question, features, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_tokens,
-                output_all_attention_masks=True, select=TASK_OUTPUT[task_id])
+    with model_lock:
+        out = model(question, features, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_tokens,
+                    output_all_attention_masks=True, select=TASK_OUTPUT[task_id])
     return _decode(task_id, out, spatials, infos)
 
 
-def prediction_batch(requests):
+def prediction_batch(requests, bucket: int = 8, select: Optional[int] = None):
     """Micro-batching across requests (the reference handles one message at a time, worker.py:664-673).
 
     `requests` is a list of argument tuples of `prediction()`.  Requests whose tensors have the same text length, region count
     and feature width go through ONE model call; every pair's forward is independent of its batch neighbours, so each answer is
     what `prediction()` returns for that request alone.  NLVR2 requests (task 12) are placed on even rows -- the binary head
-    consumes adjacent rows as one pair (worker.py:266-276) -- with a filler row in front when needed.  A request that fails
-    validation gets its exception as its answer; the others are unaffected."""
+    consumes adjacent rows as one pair (worker.py:266-276) -- with ONE filler row in front when needed.  A request that fails
+    validation gets its exception as its answer; the others are unaffected.
+
+    The engine keeps one plan (workspace + CUDA graph) per (batch, text length, regions, select): so that a long-running worker
+    sees a small, fixed set of plans, the batch is padded with filler rows to a multiple of `bucket` (even, so the binary
+    head always has whole pairs) and `select` defaults to the seven task heads whatever tasks happen to be pending."""
+    if bucket < 1:
+        raise ValueError("bucket must be >= 1")
+    fixed_select = L.OUT_TASK_HEADS if select is None else int(select)
     answers = [None] * len(requests)
     groups = {}
     for i, r in enumerate(requests):
@@ -163,25 +175,31 @@ def prediction_batch(requests):
         key = (question.shape[1], features.shape[1], features.shape[2])
         groups.setdefault(key, []).append(i)
     for idxs in groups.values():
-        rows, spans, select = [], {}, 0
+        rows, spans, need = [], {}, 0
         n = 0
         for i in idxs:
             (question, features, spatials, segment_ids, input_mask, image_mask, co_mask, task_tokens, task_id, infos) = requests[i]
             q, im, seg, tk = _expand_text(task_id, features.size(0), question, input_mask, segment_ids, task_tokens)
-            if task_id == "12" and n % 2 == 1:            # filler so that the pair starts on an even row
-                rows.append(rows[-1])
-                n += rows[-1][1].size(0)
+            if task_id == "12" and n % 2 == 1:            # ONE filler row so that the pair starts on an even row
+                rows.append(tuple(t[-1:] for t in rows[-1]))
+                n += 1
             if co_mask is None:
                 co_mask = torch.zeros(features.size(0), features.size(1), question.size(1), device=features.device)
             rows.append((q, features, spatials, seg, im, image_mask, co_mask, tk))
             spans[i] = (n, n + features.size(0))
             n += features.size(0)
-            select |= TASK_OUTPUT[task_id]
-        if n % 2 == 1 and (select & L.OUT_VIL_BINARY_PREDICTION):
-            rows.append(tuple(t[-1:] for t in rows[-1]))   # the binary head needs an even number of rows
-            n += 1
+            need |= TASK_OUTPUT[task_id]
+        sel = fixed_select | need
+        target = -(-n // bucket) * bucket
+        if target % 2 == 1 and (sel & L.OUT_VIL_BINARY_PREDICTION):
+            target += 1                                    # the binary head needs an even number of rows
+        if target > n:                                     # filler rows: copies of the last row, results discarded
+            last = tuple(t[-1:] for t in rows[-1])
+            rows.append(tuple(t.expand(target - n, *t.shape[1:]) for t in last))
+            n = target
         cat = [torch.cat([r[k] for r in rows], dim=0) for k in range(8)]
-        out = model(*cat, output_all_attention_masks=True, select=select)
+        with model_lock:
+            out = model(*cat, output_all_attention_masks=True, select=sel)
         for i in idxs:
             lo, hi = spans[i]
             task_id, infos, spatials = requests[i][8], requests[i][9], requests[i][2]
@@ -282,10 +300,10 @@ class MicroBatchWorker(object):
     for up to `max_rows` image rows, runs them through `prediction_batch` (one model call per shape group) and resolves the
     futures; a failing request resolves to its exception, like the try/except of callback (worker.py:653-655)."""
 
-    def __init__(self, max_rows: int = 64, max_wait_ms: float = 2.0):
+    def __init__(self, max_rows: int = 64, max_wait_ms: float = 2.0, bucket: int = 8):
         import queue
         import threading
-        self.max_rows, self.max_wait = int(max_rows), float(max_wait_ms) * 1e-3
+        self.max_rows, self.max_wait, self.bucket = int(max_rows), float(max_wait_ms) * 1e-3, int(bucket)
         self._q = queue.Queue()
         self._stop = False
         self.batches = []                      # rows per model call group, for tests / monitoring
@@ -293,15 +311,29 @@ class MicroBatchWorker(object):
         self._thread.start()
 
     def submit(self, body: dict, features, infos):
-        from concurrent.futures import Future
+        from concurrent.futures import CancelledError, Future
         fut = Future()
+        if self._stop:
+            fut.set_exception(CancelledError("MicroBatchWorker closed"))
+            return fut
         self._q.put((body, features, infos, fut))
         return fut
 
     def close(self):
+        """Stop the consumer thread.  Messages still queued (behind the sentinel, or submitted after close) are cancelled:
+        their futures raise `concurrent.futures.CancelledError` instead of blocking their callers for ever."""
+        import queue
+        from concurrent.futures import CancelledError
         self._stop = True
         self._q.put(None)
-        self._thread.join(timeout=10.0)
+        self._thread.join(timeout=30.0)
+        while True:
+            try:
+                item = self._q.get_nowait()
+            except queue.Empty:
+                break
+            if item is not None and not item[3].done():
+                item[3].set_exception(CancelledError("MicroBatchWorker closed"))
 
     def _loop(self):
         import queue
@@ -340,7 +372,7 @@ class MicroBatchWorker(object):
         if not reqs:
             return
         try:
-            answers = prediction_batch(reqs)
+            answers = prediction_batch(reqs, bucket=self.bucket)
         except Exception as e:                 # noqa: BLE001
             for _, fut, _ in live:
                 fut.set_exception(e)
