@@ -212,16 +212,7 @@ def prediction_batch(requests, bucket: int = 8, select: Optional[int] = None):
 
 def build_inputs(query, task, features, infos, device, tok=None):
     """The tensor construction half of custom_prediction (worker.py:402-455), returned instead of consumed."""
-    tok = tok if tok is not None else tokenizer
-    if tok is None:
-        raise L.VilbertB200Error("no tokenizer: pass vocab_file= (bert-base-uncased vocab.txt) to load_vilbert_model")
-    tokens = tok.encode(query)
-    tokens = tok.add_special_tokens_single_sentence(tokens)
-    segment_ids = [0] * len(tokens)
-    input_mask = [1] * len(tokens)
-    if len(tokens) < MAX_LENGTH:                       # pad, never truncate (worker.py:408-414)
-        pad = [0] * (MAX_LENGTH - len(tokens))
-        tokens, input_mask, segment_ids = tokens + pad, input_mask + pad, segment_ids + pad
+    tokens, input_mask, segment_ids = tokenize_query(query, tok)
     text = torch.tensor(tokens, dtype=torch.long, device=device).unsqueeze(0)
     input_mask = torch.tensor(input_mask, dtype=torch.long, device=device).unsqueeze(0)
     segment_ids = torch.tensor(segment_ids, dtype=torch.long, device=device).unsqueeze(0)
@@ -250,12 +241,49 @@ def build_inputs(query, task, features, infos, device, tok=None):
     return text, features_t, spatials, segment_ids, input_mask, image_mask, co_attention_mask, task_t
 
 
+def tokenize_query(query, tok=None):
+    """worker.py:402-414: encode, add [CLS]/[SEP], pad (never truncate) to 37 -> (tokens, input_mask, segment_ids) lists."""
+    tok = tok if tok is not None else tokenizer
+    if tok is None:
+        raise L.VilbertB200Error("no tokenizer: pass vocab_file= (bert-base-uncased vocab.txt) to load_vilbert_model")
+    tokens = tok.add_special_tokens_single_sentence(tok.encode(query))
+    segment_ids, input_mask = [0] * len(tokens), [1] * len(tokens)
+    if len(tokens) < MAX_LENGTH:
+        pad = [0] * (MAX_LENGTH - len(tokens))
+        tokens, input_mask, segment_ids = tokens + pad, input_mask + pad, segment_ids + pad
+    return tokens, input_mask, segment_ids
+
+
 def custom_prediction(query, task, features, infos, task_id):
-    """worker.py:388-458 (the GuessWhat dialog rewrite at 391-400 builds `tokens` and then discards it)."""
+    """worker.py:388-458 (the GuessWhat dialog rewrite at 391-400 builds `tokens` and then discards it).
+
+    The image half of the reference's tensor construction (global mean row, cat, box normalisation, [0,0,1,1,1], masks,
+    stack -- worker.py:422-453) runs inside the engine's region-pack kernel: the detector's box features go to the device
+    as they are and are written straight into the image-embedding GEMM's 16-bit operand (`model.forward_regions`).  Images
+    with different box counts -- which `torch.stack` at worker.py:452 cannot take -- are padded and masked."""
+    _validate(task_id, infos)
     device = torch.device("cuda", model._device)
-    text, feats, spatials, segment_ids, input_mask, image_mask, co_mask, task_t = build_inputs(query, task, features,
-                                                                                              infos, device)
-    return prediction(text, feats, spatials, segment_ids, input_mask, image_mask, co_mask, task_t, task_id, infos)
+    tokens, input_mask, segment_ids = tokenize_query(query)
+    n_img = len(infos)
+    rep = n_img if task_id in PAIR_TASKS + RETRIEVAL_TASKS else 1          # text repeated per image (worker.py:266-284)
+    text = torch.tensor([tokens] * rep, dtype=torch.long)
+    mask_t = torch.tensor([input_mask] * rep, dtype=torch.long)
+    seg_t = torch.tensor([segment_ids] * rep, dtype=torch.long)
+    task_t = torch.tensor(np.array(task), dtype=torch.long).view(1, -1)[:, :1].repeat(rep, 1)
+    counts = [int(f.shape[0]) for f in features]
+    n = max(counts)
+    feats = torch.zeros(n_img, n, features[0].shape[1], dtype=torch.float32)
+    boxes = torch.zeros(n_img, n, 4, dtype=torch.float32)
+    for i, (f, info) in enumerate(zip(features, infos)):
+        feats[i, :counts[i]] = torch.as_tensor(f, dtype=torch.float32)
+        boxes[i, :counts[i]] = torch.as_tensor(np.asarray(info["bbox"], dtype=np.float32))[:counts[i], :4]
+    wh = torch.tensor([[float(info["image_width"]), float(info["image_height"])] for info in infos], dtype=torch.float32)
+    num_boxes = None if min(counts) == n else torch.tensor(counts, dtype=torch.int32)
+    with model_lock:
+        out, spatials = model.forward_regions(text.to(device), seg_t.to(device), mask_t.to(device), task_t.to(device),
+                                              feats.to(device), boxes.to(device), wh.to(device), num_boxes,
+                                              select=TASK_OUTPUT[task_id], output_all_attention_masks=True)
+    return _decode(task_id, out, spatials, infos)
 
 
 def shape_result(task_id: str, answer, image_path: Sequence[str], image_names: Optional[List[str]] = None):
