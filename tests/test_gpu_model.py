@@ -244,6 +244,8 @@ def test_full_model_golden(full_engines, parity_log):
     assert files, "no golden fixtures committed"
     for fn in files:
         z = np.load(os.path.join(gdir, fn))
+        if int(z["weight_seed"]) != 42:
+            continue          # fixtures of a real checkpoint (make_golden_from_upstream.py --checkpoint) need that checkpoint
         B, Tin, V, seed, pad = (int(z[k]) for k in ("B", "Tin", "V", "seed", "pad"))
         inp = R.make_inputs(B, Tin, V, seed=seed, pad_regions=pad)
         out = full_engines["fp16"](*[t.cuda() for t in inp])

@@ -165,12 +165,34 @@ def test_golden_vectors_reproduce(full_oracle):
     assert len(files) >= 3
     for fn in files:
         z = np.load(os.path.join(GOLDEN, fn))
+        if int(z["weight_seed"]) != 42:
+            continue          # made from a real checkpoint by make_golden_from_upstream.py --checkpoint: needs that file
+        # (upstream_*.npz written by make_golden_from_upstream.py on the synthetic weights are REFERENCE outputs: the day they
+        # are committed this very loop pins the oracle to the reference)
         inp = R.make_inputs(int(z["B"]), int(z["Tin"]), int(z["V"]), seed=int(z["seed"]), pad_regions=int(z["pad"]))
         out = full_oracle(*inp, compute_pretraining_heads=False)
         for i, n in names.items():
             ref = torch.from_numpy(z[n])
             scale = max(1.0, float(ref.abs().max()))
             assert torch.allclose(out[i], ref, atol=2e-4 * scale), (fn, n, float((out[i] - ref).abs().max()))
+
+
+def test_upstream_repin_recipe_reports_what_is_missing():
+    """tests/golden/make_golden_from_upstream.py is the committed recipe that turns "parity unpinned" into reference-pinned
+    fixtures once `vilbert` is importable (worker.py:44-46).  Here it is not: the script must say so and exit 3, without writing."""
+    import subprocess
+    import sys
+    before = set(os.listdir(GOLDEN))
+    r = subprocess.run([sys.executable, os.path.join(GOLDEN, "make_golden_from_upstream.py")], capture_output=True, text=True, timeout=300)
+    try:
+        import vilbert.vilbert  # noqa: F401
+        have = True
+    except Exception:
+        have = False
+    if not have:
+        assert r.returncode == 3, (r.returncode, r.stdout[-400:], r.stderr[-400:])
+        assert "vilbert.vilbert" in r.stdout and "unpinned" in r.stdout
+        assert set(os.listdir(GOLDEN)) == before
 
 
 def test_synthetic_checkpoint_loads_into_oracle():
