@@ -130,6 +130,11 @@ typedef struct {
                                       fp32 accumulator; attention runs in fp32 on CUDA cores; GELU uses the 1.5e-7 erf.  3x the
                                       tensor work of the default mode -- for logit parity with the reference's fp32 forward
                                       (<= 1e-3 per logit, BASELINE.json north_star), not for throughput.  Implies act_fp16. */
+    int32_t ln_fold;               /* default on (-1: off): LayerNorm folded into the GEMMs around it.  The GEMM that produces
+                                      u = dense(x) + residual writes u (fp32 + 16-bit) and per-row (mean, M2) statistics instead of
+                                      LayerNorm(u); the next GEMM runs on u with weights pre-scaled by gamma and finishes with
+                                      rstd * (acc - mean * s) + c; residual readers rebuild LayerNorm(u) on the fly.  Same math,
+                                      58 of a forward's 62 LayerNorm launches gone.  Off in split_fp32 / fused_layernorm modes. */
     int32_t max_plans;             /* plan-cache bound: plans (workspace + CUDA graph per (batch, tokens, regions, select, slot))
                                       beyond this are evicted least-recently-used; 0 -> 24 */
 } vb200_options;
@@ -248,6 +253,16 @@ int vb200_linear_split(const void* x16, int64_t ld_x, const void* w16, int64_t l
 int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
                     float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
                     int32_t act_fp16, void* cuda_stream);
+/* The GEMM with the LayerNorm fold epilogues (vilbert-multi-task_b200/csrc/gemm_persistent.cuh, row_stats).  Statistics arrays are
+ * float2 (mean, M2 = sum (x - mean)^2) per row and 32-column chunk, laid out [N_src / 32][stats_ld].
+ * mode 5 (producer): u = x w^T + bias + residual, where the residual is res, or LayerNorm_{res_gamma,res_beta}(res) rebuilt from
+ *         res_stats when that is non-NULL; writes u to y_f32 AND y16, and its statistics to out_stats.
+ * mode 4 (consumer): x holds such a u, w = gamma o W (16-bit), fold_s[n] = sum_k w[n,k], bias = c;
+ *         y = act(rstd * (x w^T - mean * s) + c), mean / rstd from a_stats (a_parts = K_logical / 32). */
+int vb200_linear_ln(const void* x16, int64_t ld_x, const void* w16, int64_t ld_w, const float* bias, int32_t mode, const void* a_stats,
+                    int32_t a_parts, const float* fold_s, const float* res, int64_t ld_res, const void* res_stats, int32_t res_parts,
+                    const float* res_gamma, const float* res_beta, void* out_stats, int32_t stats_ld, float eps, int32_t act, void* y16,
+                    int64_t ld_y16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K, int32_t act_fp16, void* cuda_stream);
 /* split16 != 0: out_16 is the fp16 hi | lo | hi operand (stride ld_16 of the 3x wider buffer). */
 int vb200_layernorm_split(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
                           float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N, void* cuda_stream);

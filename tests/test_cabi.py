@@ -38,7 +38,7 @@ def test_ctypes_structs_match_header_layout():
     assert C.sizeof(L.Tensor) == 8 + 4 + 4 + 16 + 8
     assert C.sizeof(L.Inputs) == 16 + 8 * 8
     assert C.sizeof(L.Outputs) == 13 * 8
-    assert C.sizeof(L.Options) == 36
+    assert C.sizeof(L.Options) == 40
     assert C.sizeof(L.RegionInputs) == 16 + 9 * 8
 
 

@@ -376,3 +376,75 @@ def test_attention_f32(B, Lq, Lk, heads, d, in_kind, parity_log):
             cerr = (ctx.float() - c_ref).abs().max().item()
             assert cerr < (4e-3 if ctx_mode == 1 else 3e-2), cerr
     parity_log(test="attention_f32", B=B, Lq=Lq, Lk=Lk, heads=heads, d=d, in_kind=in_kind, probs_max_abs_err=perr)
+
+
+@pytest.mark.parametrize("act_dt", ACT)
+@pytest.mark.parametrize("M,H,N2,act", [(300, 256, 384, 0), (1984, 768, 3072, 1), (2304, 1024, 1024, 0), (64, 1024, 256, 1)])
+def test_layernorm_fold_chain(M, H, N2, act, act_dt, parity_log):
+    """LayerNorm folded into its neighbours: producer GEMM (mode 5: u = x W1^T + b1 + residual, fp32 + 16-bit u, row statistics),
+    then (a) a consumer GEMM (mode 4) on u with gamma-scaled weights, (b) a second producer whose residual is LayerNorm(u)
+    rebuilt from the statistics, (c) the row-LayerNorm kernel with the same pending residual -- all against fp64 torch math
+    that materialises LayerNorm(u)."""
+    L, lib = _lib()
+    f16 = 1 if act_dt == torch.float16 else 0
+    g = torch.Generator(device="cuda").manual_seed(17)
+    K1 = 256
+    x = torch.randn(M, K1, generator=g, device="cuda").to(act_dt)
+    w1 = (torch.randn(H, K1, generator=g, device="cuda") / math.sqrt(K1)).to(act_dt)
+    b1 = 0.1 * torch.randn(H, generator=g, device="cuda")
+    r0 = torch.randn(M, H, generator=g, device="cuda")                       # a plain (final) residual for the first producer
+    gamma = 1 + 0.1 * torch.randn(H, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(H, generator=g, device="cuda")
+    w2 = torch.randn(N2, H, generator=g, device="cuda") / math.sqrt(H)
+    b2 = 0.1 * torch.randn(N2, generator=g, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ld = (M + 31) // 32 * 32
+    stats = torch.zeros(H // 32, ld, 2, device="cuda")
+    u32 = torch.empty(M, H, device="cuda")
+    u16 = torch.empty(M, H, dtype=act_dt, device="cuda")
+    L.check(lib.vb200_linear_ln(_ptr(x), K1, _ptr(w1), K1, _ptr(b1), 5, None, 0, None, _ptr(r0), H, None, 0, None, None, _ptr(stats), ld,
+                                1e-12, 0, _ptr(u16), H, _ptr(u32), H, M, H, K1, f16, st), None)
+    torch.cuda.synchronize()
+    u_ref = (x.double() @ w1.double().t() + b1.double() + r0.double())
+    assert (u32.double() - u_ref).abs().max().item() < 2e-3
+    mean_ref, var_ref = u32.double().mean(1), u32.double().var(1, unbiased=False)
+    cm, m2 = stats[:, :M, 0].double(), stats[:, :M, 1].double()
+    mean = cm.mean(0)
+    var = (m2 + 32 * (cm - mean) ** 2).sum(0) / H
+    assert (mean - mean_ref).abs().max().item() < 1e-5 and ((var - var_ref).abs() / var_ref).max().item() < 1e-5
+    ln_ref = (u32.double() - mean_ref[:, None]) / torch.sqrt(var_ref[:, None] + 1e-12) * gamma.double() + beta.double()
+    # (a) consumer: y = act(LayerNorm(u) W2^T + b2) from the 16-bit u and gamma-scaled 16-bit weights
+    w2f = (w2 * gamma[None, :]).to(act_dt)
+    s = w2f.float().sum(1).contiguous()
+    c = (w2.double() @ beta.double() + b2.double()).float().contiguous()
+    y16 = torch.empty(M, N2, dtype=act_dt, device="cuda")
+    L.check(lib.vb200_linear_ln(_ptr(u16), H, _ptr(w2f), H, _ptr(c), 4, _ptr(stats), H // 32, _ptr(s), None, 0, None, 0, None, None, None, ld,
+                                1e-12, act, _ptr(y16), N2, None, 0, M, N2, H, f16, st), None)
+    torch.cuda.synchronize()
+    y_ref = ln_ref @ w2.double().t() + b2.double()
+    if act == 1:
+        y_ref = y_ref * 0.5 * (1.0 + torch.erf(y_ref / math.sqrt(2.0)))
+    err_a = (y16.double() - y_ref).abs().max().item()
+    # what the unfolded path gives at the same operand precision: LayerNorm(u) rounded to 16 bits, W2 rounded to 16 bits
+    y_plain = ln_ref.to(act_dt).double() @ w2.to(act_dt).double().t() + b2.double()
+    if act == 1:
+        y_plain = y_plain * 0.5 * (1.0 + torch.erf(y_plain / math.sqrt(2.0)))
+    err_plain = (y_plain.to(act_dt).double() - y_ref).abs().max().item()
+    parity_log(test="ln_fold_consumer", M=M, H=H, N=N2, act=act, dtype=str(act_dt), max_abs_err=err_a, unfolded_same_precision=err_plain)
+    assert err_a < max(3.0 * err_plain, 4e-3 if f16 else 3e-2), (err_a, err_plain)
+    # (b) producer with a pending residual: u2 = inter W3^T + b3 + LayerNorm(u)
+    K3 = 128
+    xi = torch.randn(M, K3, generator=g, device="cuda").to(act_dt)
+    w3 = (torch.randn(H, K3, generator=g, device="cuda") / math.sqrt(K3)).to(act_dt)
+    stats2 = torch.zeros(H // 32, ld, 2, device="cuda")
+    v32 = torch.empty(M, H, device="cuda")
+    v16 = torch.empty(M, H, dtype=act_dt, device="cuda")
+    L.check(lib.vb200_linear_ln(_ptr(xi), K3, _ptr(w3), K3, _ptr(b1), 5, None, 0, None, _ptr(u32), H, _ptr(stats), H // 32, _ptr(gamma),
+                                _ptr(beta), _ptr(stats2), ld, 1e-12, 0, _ptr(v16), H, _ptr(v32), H, M, H, K3, f16, st), None)
+    torch.cuda.synchronize()
+    v_ref = xi.double() @ w3.double().t() + b1.double() + ln_ref
+    err_b = (v32.double() - v_ref).abs().max().item()
+    assert err_b < 2e-3, err_b
+    assert (v16.double() - v_ref).abs().max().item() < (1e-2 if f16 else 8e-2)
+    # (c) the row-LayerNorm kernel with the same pending residual is exercised through the model tests (boundary layers)
+    parity_log(test="ln_fold_producer", M=M, H=H, dtype=str(act_dt), max_abs_err=err_b)

@@ -360,3 +360,32 @@ def test_micro_batch_worker_on_engine(full_oracle, full_h):
         else:
             assert r["result"]["image_name_list"] == w["image_name_list"]
             assert r["result"]["confidence_list"] == pytest.approx(w["confidence_list"], abs=0.3)
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm fold
+def test_layernorm_fold_vs_unfolded_and_oracle(tiny_oracle, full_oracle, parity_log):
+    """Default engine (58 LayerNorms folded into the GEMMs around them) vs the round-1 form (every LayerNorm as GEMM + row kernel):
+    both within the fp16 tolerance of the fp32 oracle, and the launch count of a forward drops accordingly."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import _lib as L
+    for tag, oracle, inp in (("tiny", tiny_oracle, _tiny_inputs(tiny_oracle, 3, 30, 36, 91, pad=2)),
+                             ("full", full_oracle, list(R.make_inputs(3, 30, 36, seed=92, pad_regions=2)))):
+        ref = oracle(*inp, compute_pretraining_heads=True)
+        dev = [t.cuda() for t in inp]
+        fold, plain = _engine(oracle), _engine(oracle, ln_fold=False)
+        a = fold(*dev, compute_pretraining_heads=True)
+        b = plain(*dev, compute_pretraining_heads=True)
+        torch.cuda.synchronize()
+        ea, eb = _max_err(ref, a), _max_err(ref, b)
+        for name in ea:
+            parity_log(test="ln_fold_" + tag, output=name, err_fold_vs_fp32=ea[name][0], err_unfolded_vs_fp32=eb[name][0], ref_std=ea[name][1])
+            assert ea[name][0] < 1e-2, (tag, name, ea[name][0])
+        n_fold, _ = fold.plan_info(64, 30, 36, L.OUT_VIL_PREDICTION)
+        n_plain, _ = plain.plan_info(64, 30, 36, L.OUT_VIL_PREDICTION)
+        parity_log(test="ln_fold_launches_" + tag, launches_fold=n_fold, launches_unfolded=n_plain)
+        assert n_plain - n_fold == 58 and n_fold <= 160
+        # a pair's logits still do not depend on its batch neighbours
+        one = fold(*[t[1:2] for t in dev])
+        assert torch.equal(one[0], a[0][1:2])
+        fold.close()
+        plain.close()

@@ -61,14 +61,14 @@ class Outputs(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_labels", C.c_int32), ("use_cuda_graph", C.c_int32),
                 ("use_pdl", C.c_int32), ("strict", C.c_int32), ("act_fp16", C.c_int32),
-                ("fused_layernorm", C.c_int32), ("split_fp32", C.c_int32), ("max_plans", C.c_int32)]
+                ("fused_layernorm", C.c_int32), ("split_fp32", C.c_int32), ("ln_fold", C.c_int32), ("max_plans", C.c_int32)]
 
 
 # every symbol include/vilbert_b200.h declares (tests/test_cabi.py checks the list against the header)
 EXPORTS = ["vb200_abi_version", "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_forward", "vb200_forward_slot",
            "vb200_forward_host", "vb200_forward_host_slot", "vb200_plan_info", "vb200_model_dim", "vb200_profile_ops",
            "vb200_attention_layout", "vb200_forward_regions", "vb200_encode_text", "vb200_encode_image", "vb200_forward_cached",
-           "vb200_linear", "vb200_linear_split", "vb200_layernorm", "vb200_layernorm_split", "vb200_attention_f32",
+           "vb200_linear", "vb200_linear_split", "vb200_linear_ln", "vb200_layernorm", "vb200_layernorm_split", "vb200_attention_f32",
            "vb200_self_attention", "vb200_co_attention"]
 
 _lib = None
@@ -111,6 +111,8 @@ def load():
     lib.vb200_encode_image.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.vb200_forward_cached.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, C.POINTER(Outputs), u32, i32, vp]
     lib.vb200_linear_split.argtypes = [vp, i64, vp, i64, vp, i32, vp, i64, vp, i64, i64, i64, i64, vp]
+    lib.vb200_linear_ln.argtypes = [vp, i64, vp, i64, vp, i32, vp, i32, vp, vp, i64, vp, i32, vp, vp, vp, i32, f32, i32, vp, i64, vp, i64,
+                                    i64, i64, i64, i32, vp]
     lib.vb200_layernorm_split.argtypes = [vp, i64, vp, i64, vp, vp, f32, vp, i64, vp, i64, i64, i64, vp]
     lib.vb200_attention_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp, i32, i32, i32, i32, i32, vp, i64, i32, vp, vp]
     lib.vb200_linear.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, f32, i32, vp, i64, vp, i64,

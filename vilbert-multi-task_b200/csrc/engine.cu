@@ -219,6 +219,7 @@ inline uint16_t f32_to_bf16_bits(float f) {
     u += 0x7fffu + ((u >> 16) & 1u);                                                          // round to nearest even
     return static_cast<uint16_t>(u >> 16);
 }
+inline float bf16_bits_to_f32(uint16_t h) { uint32_t u = static_cast<uint32_t>(h) << 16; float f; memcpy(&f, &u, 4); return f; }
 inline float half_bits_to_f32(uint16_t h) {
     const uint32_t sign = (h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ff;
     uint32_t u;
@@ -253,8 +254,12 @@ struct LinearW {            // nn.Linear [N, K] -> bf16 [N, ldw] (K zero-padded 
     bf16* w = nullptr;
     float* bias = nullptr;
     int N = 0, K = 0, ldw = 0;
+    // LayerNorm fold (gemm_persistent.cuh row_stats): this Linear's input is LayerNorm_{g,b}(u) of a pending LayerNorm; then
+    // w = g o W (16-bit), bias = c = sum_k b_k W[n,k] + bias_n, fold_s = s = sum_k w[n,k]; fold_g identifies that LayerNorm
+    float* fold_s = nullptr;
+    const float* fold_g = nullptr;
 };
-struct LNW { float* g = nullptr; float* b = nullptr; int n = 0; };
+struct LNW { float* g = nullptr; float* b = nullptr; int n = 0; std::vector<float> hg, hb; };   // hg / hb: host copies (fold)
 struct RowW { float* w = nullptr; float* b = nullptr; int n_out = 0, K = 0; };   // narrow fp32 heads
 struct LayerW { LinearW qkv, attn_out, inter, out; LNW ln1, ln2; };
 struct ConnW { LinearW qkv_img, qkv_txt, dense1, dense2, v_inter, v_out, t_inter, t_out; LNW ln1, ln2, v_ln, t_ln; };
@@ -346,6 +351,7 @@ struct Op {
     float* ln_out_f = nullptr;
     bf16* ln_out_h = nullptr;
     int ln_ld = 0, ln_M = 0, ln_N = 0;
+    vb::LnPending ln_pend{nullptr, 0, 0, nullptr, nullptr};   // residual whose own LayerNorm is still pending (LayerNorm fold)
     // rowdot
     const float *x = nullptr, *W = nullptr, *bias = nullptr, *add = nullptr;
     float* out = nullptr;
@@ -367,6 +373,9 @@ struct Plan {
     float* t_f32[2]; bf16* t_b16[2];
     float* v_f32[2]; bf16* v_b16[2];
     float* y_scratch[2] = {nullptr, nullptr};   // per-stream fp32 GEMM output feeding the un-fused LayerNorm kernel
+    float2* t_stats[2] = {nullptr, nullptr};    // LayerNorm fold: per-row (mean, M2) per 32 columns of t_f32[i] / v_f32[i],
+    float2* v_stats[2] = {nullptr, nullptr};    //   [hidden / 32][stats_ld] (gemm_persistent.cuh row_stats)
+    int stats_ld_t = 0, stats_ld_v = 0;
     int t_cur = 0, v_cur = 0;
     std::vector<Op> ops;
     OutBuf outs[12];
@@ -395,6 +404,9 @@ struct vb200_engine {
     vb200_options opt{};
     int num_labels = 0, gqa_labels = 0;
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
+    bool ln_fold = true;       // LayerNorm folded into the neighbouring GEMMs (row_stats in gemm_persistent.cuh); VB200_LNFOLD=0 /
+                               // vb200_options::ln_fold = -1: every LayerNorm as GEMM (fp32 out) + row kernel, as in round 1
+    std::set<std::string> fold_out_t, fold_out_v;   // stages ("T3", "C0", "E", ...) whose OUTPUT LayerNorm stays pending
     bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
@@ -477,15 +489,25 @@ struct vb200_engine {
         else for (int64_t i = 0; i < r * c; ++i) h[i] = t.at(i);
         return upload_f32(h);
     }
+    std::map<std::string, LNW> ln_cache;        // every LayerNorm is loaded once (a fold source is needed before its own layer)
     LNW load_ln(const std::string& prefix, int n) {
+        auto it = ln_cache.find(prefix);
+        if (it != ln_cache.end()) return it->second;
         LNW l; l.n = n;
-        l.g = load_vec(prefix + ".weight", n);
-        l.b = load_vec(prefix + ".bias", n);
+        HostTensor& tg = need(prefix + ".weight", 1, n);
+        HostTensor& tb = need(prefix + ".bias", 1, n);
+        if (!dry) {
+            l.hg.resize(n); l.hb.resize(n);
+            for (int i = 0; i < n; ++i) { l.hg[i] = tg.at(i); l.hb[i] = tb.at(i); }
+            l.g = upload_f32(l.hg);
+            l.b = upload_f32(l.hb);
+        }
+        ln_cache[prefix] = l;
         return l;
     }
     // one or several nn.Linear stacked along N (fused QKV), optional extra K columns from a second weight
     LinearW load_linear(const std::vector<std::string>& prefixes, int64_t n_each, int64_t k,
-                        const std::string& extra_k_prefix = "", int64_t extra_k = 0) {
+                        const std::string& extra_k_prefix = "", int64_t extra_k = 0, const LNW* fold = nullptr) {
         LinearW L;
         L.N = static_cast<int>(n_each * prefixes.size());
         L.K = static_cast<int>(k + (extra_k ? 64 : 0));
@@ -499,6 +521,34 @@ struct vb200_engine {
         if (x3) { load_linear_split(L, prefixes, n_each, k, extra_k_prefix, extra_k); return L; }
         std::vector<uint16_t> h(static_cast<size_t>(L.N) * L.ldw, 0);
         std::vector<float> hb(L.N, 0.0f);
+        if (fold != nullptr) {
+            // LayerNorm fold: W' = g o W in 16 bits, s_n = sum of the ROUNDED W'[n,:] (so the mean term cancels exactly against
+            // what the tensor cores multiply), c_n = sum_k b_k W[n,k] + bias_n
+            if (extra_k || static_cast<int64_t>(fold->hg.size()) != k) fail(VB200_ERR_INVALID, "LayerNorm fold: width mismatch");
+            std::vector<float> hs(L.N, 0.0f);
+            for (size_t pi = 0; pi < prefixes.size(); ++pi) {
+                HostTensor& w = need(prefixes[pi] + ".weight", 2, n_each, k);
+                HostTensor& b = need(prefixes[pi] + ".bias", 1, n_each);
+                for (int64_t n = 0; n < n_each; ++n) {
+                    uint16_t* dst = &h[(pi * n_each + n) * L.ldw];
+                    double sn = 0.0, cn = 0.0;
+                    for (int64_t j = 0; j < k; ++j) {
+                        const float wv = w.at(n * k + j);
+                        dst[j] = cvt16(wv * fold->hg[j]);
+                        sn += static_cast<double>(f16 ? half_bits_to_f32(dst[j]) : bf16_bits_to_f32(dst[j]));
+                        cn += static_cast<double>(fold->hb[j]) * static_cast<double>(wv);
+                    }
+                    hs[pi * n_each + n] = static_cast<float>(sn);
+                    hb[pi * n_each + n] = static_cast<float>(cn + static_cast<double>(b.at(n)));
+                }
+            }
+            L.w = weights.alloc_n<bf16>(h.size());
+            CUDA_CHECK(cudaMemcpy(L.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+            L.bias = upload_f32(hb);
+            L.fold_s = upload_f32(hs);
+            L.fold_g = fold->g;
+            return L;
+        }
         for (size_t pi = 0; pi < prefixes.size(); ++pi) {
             HostTensor& w = need(prefixes[pi] + ".weight", 2, n_each, k);
             HostTensor& b = need(prefixes[pi] + ".bias", 1, n_each);
@@ -561,21 +611,24 @@ struct vb200_engine {
         CUDA_CHECK(cudaMemcpy(L.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
         L.bias = upload_f32(hb);
     }
-    LinearW load_linear1(const std::string& prefix, int64_t n, int64_t k) { return load_linear({prefix}, n, k); }
+    LinearW load_linear1(const std::string& prefix, int64_t n, int64_t k, const LNW* fold = nullptr) {
+        return load_linear({prefix}, n, k, "", 0, fold);
+    }
     RowW load_row(const std::string& prefix, int n_out, int k) {
         RowW r; r.n_out = n_out; r.K = k;
         r.w = load_mat_f32(prefix + ".weight", n_out, k);
         r.b = load_vec(prefix + ".bias", n_out);
         return r;
     }
-    LayerW load_layer(const std::string& p, int hid, int inter) {
+    // src: the pending LayerNorm of this layer's input (previous stage of the stream) when that one is folded, else null
+    LayerW load_layer(const std::string& p, int hid, int inter, const LNW* src) {
         LayerW L;
-        L.qkv = load_linear({p + ".attention.self.query", p + ".attention.self.key", p + ".attention.self.value"}, hid, hid);
-        L.attn_out = load_linear1(p + ".attention.output.dense", hid, hid);
         L.ln1 = load_ln(p + ".attention.output.LayerNorm", hid);
-        L.inter = load_linear1(p + ".intermediate.dense", inter, hid);
-        L.out = load_linear1(p + ".output.dense", hid, inter);
         L.ln2 = load_ln(p + ".output.LayerNorm", hid);
+        L.qkv = load_linear({p + ".attention.self.query", p + ".attention.self.key", p + ".attention.self.value"}, hid, hid, "", 0, src);
+        L.attn_out = load_linear1(p + ".attention.output.dense", hid, hid);
+        L.inter = load_linear1(p + ".intermediate.dense", inter, hid, ln_fold ? &L.ln1 : nullptr);
+        L.out = load_linear1(p + ".output.dense", hid, inter);
         return L;
     }
     ClsW load_cls(const std::string& p, int in_dim, int hid, int out_dim, bool narrow) {
@@ -623,23 +676,80 @@ struct vb200_engine {
         img_emb = load_linear({"bert.v_embeddings.image_embeddings"}, c.v_hidden, c.v_feat,
                               "bert.v_embeddings.image_location_embeddings", 5);
         vemb_ln = load_ln("bert.v_embeddings.LayerNorm", c.v_hidden);
-        for (int i = 0; i < c.layers; ++i) t_layers.push_back(load_layer("bert.encoder.layer." + std::to_string(i), c.hidden, c.inter));
-        for (int i = 0; i < c.v_layers; ++i) v_layers.push_back(load_layer("bert.encoder.v_layer." + std::to_string(i), c.v_hidden, c.v_inter));
+        // [UPSTREAM] BertEncoder.forward schedule
+        {
+            int v_start = 0, t_start = 0;
+            for (size_t i = 0; i < c.v_bi_id.size(); ++i) {
+                const int v_end = c.v_bi_id[i], t_end = c.t_bi_id[i];
+                for (int k = t_start; k < t_end; ++k) schedule.push_back("T" + std::to_string(k));
+                for (int k = v_start; k < v_end; ++k) schedule.push_back("V" + std::to_string(k));
+                schedule.push_back("C" + std::to_string(i));
+                v_start = v_end; t_start = t_end;
+            }
+            for (int k = v_start; k < c.v_layers; ++k) schedule.push_back("V" + std::to_string(k));
+            for (int k = t_start; k < c.layers; ++k) schedule.push_back("T" + std::to_string(k));
+        }
+        // LayerNorm fold map (gemm_persistent.cuh row_stats).  Each stream is a chain of stages (text: T layers and the text half of
+        // the connection layers; image: the embedding, V layers, the image half of the connection layers).  A stage's OUTPUT
+        // LayerNorm stays pending -- folded into the next stage's first GEMM and rebuilt in its residual -- unless the stage is the
+        // stream's last one (poolers, heads and the output taps read real values) or the last one ahead of the first connection
+        // layer (that is where the retrieval path caches per-caption / per-image states, and every plan mode must compute the same
+        // bits).  The LayerNorm INSIDE a stage (after the attention / co-attention output projection) always folds.
+        std::vector<std::string> t_st, v_st{"E"};
+        for (const std::string& st : schedule) {
+            if (st[0] == 'T' || st[0] == 'C') t_st.push_back(st);
+            if (st[0] == 'V' || st[0] == 'C') v_st.push_back(st);
+        }
+        auto stage_ln = [&](const std::string& st, bool text) -> std::pair<std::string, int> {
+            const std::string i = st.substr(st[0] == 'E' ? 0 : 1);
+            if (st[0] == 'E') return {"bert.v_embeddings.LayerNorm", c.v_hidden};
+            if (st[0] == 'T') return {"bert.encoder.layer." + i + ".output.LayerNorm", c.hidden};
+            if (st[0] == 'V') return {"bert.encoder.v_layer." + i + ".output.LayerNorm", c.v_hidden};
+            return text ? std::make_pair("bert.encoder.c_layer." + i + ".t_output.LayerNorm", c.hidden)
+                        : std::make_pair("bert.encoder.c_layer." + i + ".v_output.LayerNorm", c.v_hidden);
+        };
+        // src_of[stage] = the previous stage's output LayerNorm if it folds, else nothing; fold_out[stage] as above
+        std::map<std::string, LNW> src_t, src_v;
+        auto walk = [&](const std::vector<std::string>& stages, bool text, std::map<std::string, LNW>& src, std::set<std::string>& folds) {
+            int first_c = -1;
+            for (size_t i = 0; i < stages.size(); ++i) if (stages[i][0] == 'C') { first_c = static_cast<int>(i); break; }
+            for (size_t i = 0; i < stages.size(); ++i) {
+                const bool fo = ln_fold && i + 1 < stages.size() && static_cast<int>(i) != first_c - 1;
+                if (fo) {
+                    folds.insert(stages[i]);
+                    auto nm = stage_ln(stages[i], text);
+                    src[stages[i + 1]] = load_ln(nm.first, nm.second);
+                }
+            }
+        };
+        walk(t_st, true, src_t, fold_out_t);
+        walk(v_st, false, src_v, fold_out_v);
+        auto src_ptr = [](std::map<std::string, LNW>& m, const std::string& st) -> const LNW* {
+            auto it = m.find(st);
+            return it == m.end() ? nullptr : &it->second;
+        };
+        for (int i = 0; i < c.layers; ++i)
+            t_layers.push_back(load_layer("bert.encoder.layer." + std::to_string(i), c.hidden, c.inter, src_ptr(src_t, "T" + std::to_string(i))));
+        for (int i = 0; i < c.v_layers; ++i)
+            v_layers.push_back(load_layer("bert.encoder.v_layer." + std::to_string(i), c.v_hidden, c.v_inter, src_ptr(src_v, "V" + std::to_string(i))));
         for (size_t i = 0; i < c.v_bi_id.size(); ++i) {
             const std::string p = "bert.encoder.c_layer." + std::to_string(i);
+            const std::string cs = "C" + std::to_string(i);
             ConnW w;
-            w.qkv_img = load_linear({p + ".biattention.query1", p + ".biattention.key1", p + ".biattention.value1"}, c.bi_hidden, c.v_hidden);
-            w.qkv_txt = load_linear({p + ".biattention.query2", p + ".biattention.key2", p + ".biattention.value2"}, c.bi_hidden, c.hidden);
-            w.dense1 = load_linear1(p + ".biOutput.dense1", c.v_hidden, c.bi_hidden);
             w.ln1 = load_ln(p + ".biOutput.LayerNorm1", c.v_hidden);
-            w.dense2 = load_linear1(p + ".biOutput.dense2", c.hidden, c.bi_hidden);
             w.ln2 = load_ln(p + ".biOutput.LayerNorm2", c.hidden);
-            w.v_inter = load_linear1(p + ".v_intermediate.dense", c.v_inter, c.v_hidden);
-            w.v_out = load_linear1(p + ".v_output.dense", c.v_hidden, c.v_inter);
             w.v_ln = load_ln(p + ".v_output.LayerNorm", c.v_hidden);
-            w.t_inter = load_linear1(p + ".t_intermediate.dense", c.inter, c.hidden);
-            w.t_out = load_linear1(p + ".t_output.dense", c.hidden, c.inter);
             w.t_ln = load_ln(p + ".t_output.LayerNorm", c.hidden);
+            w.qkv_img = load_linear({p + ".biattention.query1", p + ".biattention.key1", p + ".biattention.value1"}, c.bi_hidden, c.v_hidden,
+                                    "", 0, src_ptr(src_v, cs));
+            w.qkv_txt = load_linear({p + ".biattention.query2", p + ".biattention.key2", p + ".biattention.value2"}, c.bi_hidden, c.hidden,
+                                    "", 0, src_ptr(src_t, cs));
+            w.dense1 = load_linear1(p + ".biOutput.dense1", c.v_hidden, c.bi_hidden);
+            w.dense2 = load_linear1(p + ".biOutput.dense2", c.hidden, c.bi_hidden);
+            w.v_inter = load_linear1(p + ".v_intermediate.dense", c.v_inter, c.v_hidden, ln_fold ? &w.ln1 : nullptr);
+            w.v_out = load_linear1(p + ".v_output.dense", c.v_hidden, c.v_inter);
+            w.t_inter = load_linear1(p + ".t_intermediate.dense", c.inter, c.hidden, ln_fold ? &w.ln2 : nullptr);
+            w.t_out = load_linear1(p + ".t_output.dense", c.hidden, c.inter);
             c_layers.push_back(w);
             // [UPSTREAM] present in the checkpoint, never applied in forward
             for (const char* u : {".biOutput.q_dense1.weight", ".biOutput.q_dense1.bias", ".biOutput.q_dense2.weight", ".biOutput.q_dense2.bias"}) {
@@ -689,17 +799,7 @@ struct vb200_engine {
             if (n) fail(VB200_ERR_CHECKPOINT, "checkpoint has %d unexpected key(s):%s%s", n, extra.c_str(), n > 8 ? " ..." : "");
         }
         sd.clear();   // host pointers are the caller's; do not keep them
-        // [UPSTREAM] BertEncoder.forward schedule
-        int v_start = 0, t_start = 0;
-        for (size_t i = 0; i < c.v_bi_id.size(); ++i) {
-            const int v_end = c.v_bi_id[i], t_end = c.t_bi_id[i];
-            for (int k = t_start; k < t_end; ++k) schedule.push_back("T" + std::to_string(k));
-            for (int k = v_start; k < v_end; ++k) schedule.push_back("V" + std::to_string(k));
-            schedule.push_back("C" + std::to_string(i));
-            v_start = v_end; t_start = t_end;
-        }
-        for (int k = v_start; k < c.v_layers; ++k) schedule.push_back("V" + std::to_string(k));
-        for (int k = t_start; k < c.layers; ++k) schedule.push_back("T" + std::to_string(k));
+        ln_cache.clear();
     }
 
     // ---------------------------------------------------------------- plan construction
@@ -710,11 +810,26 @@ struct vb200_engine {
     // All sizes are LOGICAL (elements of the mathematical matrices).  In fp32-parity mode (x3) every 16-bit operand buffer is
     // physically 3x as wide (fp16 hi | lo | hi per 64 columns), so operand strides, the contraction length and the 16-bit
     // output stride are multiplied by S = 3 here and nowhere else.
+    // LayerNorm fold (row_stats in gemm_persistent.cuh): what add_linear needs to know beyond the plain call
+    struct FoldArgs {
+        const float2* a_stats = nullptr;   // the A operand's LayerNorm is pending: its row statistics (W must be a folded Linear)
+        int a_parts = 0;
+        const float2* res_stats = nullptr; // the residual's LayerNorm is pending: its statistics and parameters
+        int res_parts = 0;
+        const LNW* res_ln = nullptr;
+        float2* out_stats = nullptr;       // keep THIS Linear's LayerNorm pending: write u (fp32 + 16-bit) and its statistics here
+        int stats_ld = 0;
+    };
     void add_linear(Plan& pl, const bf16* A, int64_t a_rows, int64_t lda, const LinearW& W, int act, const float* res, int ld_res,
                     const LNW* ln, bf16* out_b, int ld_b, float* out_f, int ld_f, int stream = 0, Op::Sync sync = Op::NONE,
-                    const float* mul = nullptr, int ld_mul = 0) {
+                    const float* mul = nullptr, int ld_mul = 0, const FoldArgs* fa = nullptr) {
         const int S = x3 ? 3 : 1;
-        const bool split_ln = ln != nullptr && !fused_ln;
+        const bool keep_pending = ln != nullptr && fa != nullptr && fa->out_stats != nullptr;
+        const bool fold_in = fa != nullptr && fa->a_stats != nullptr;
+        if ((W.fold_s != nullptr) != fold_in)
+            fail(VB200_ERR_INVALID, "LayerNorm fold: Linear N=%d K=%d was %s with a pending LayerNorm but its input is %s", W.N, W.K,
+                 W.fold_s ? "folded" : "not folded", fold_in ? "pending" : "final");
+        const bool split_ln = ln != nullptr && !fused_ln && !keep_pending;
         if (x3 && act == vb::kActGelu) act = vb::kActGeluExact;
         Op op{};
         op.kind = Op::GEMM;
@@ -723,7 +838,7 @@ struct vb200_engine {
         op.ln = ln != nullptr && !split_ln;
         op.block_n = vb::gemm_p_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
-        if (!x3 && !op.ln && a_rows >= 256) {
+        if (!x3 && !op.ln && !keep_pending && !fold_in && a_rows >= 256) {
             if (pair_bn > 0) op.pair = W.N % pair_bn == 0;
             else if (pair_bn < 0) op.pair = W.N % 256 == 0 && ((a_rows + 255) / 256) * (W.N / 256) >= 4 * (vb::num_sms_host() / 2);
             if (op.pair) op.block_n = pair_bn > 0 ? pair_bn : 256;
@@ -735,8 +850,18 @@ struct vb200_engine {
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw * S;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : (opt.use_pdl ? (early_w ? 5 : 1) : 0);
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
+        if (fold_in) {
+            e.ln_mode = 4; e.a_stats = fa->a_stats; e.a_parts = fa->a_parts; e.fold_s = W.fold_s; e.stats_ld = fa->stats_ld;
+        }
         if (split_ln) {
             e.out_f32 = pl.y_scratch[stream]; e.ld_f32 = W.N;
+        } else if (keep_pending) {
+            // producer of a pending LayerNorm: u = acc + bias + residual in fp32 and 16 bits, plus the row statistics
+            e.ln_mode = 5; e.res = res; e.ld_res = ld_res;
+            e.res_stats = fa->res_stats; e.res_parts = fa->res_parts;
+            e.res_gamma = fa->res_ln ? fa->res_ln->g : nullptr; e.res_beta = fa->res_ln ? fa->res_ln->b : nullptr;
+            e.out_stats = fa->out_stats; e.stats_ld = fa->stats_ld;
+            e.out_bf16 = out_b; e.ld_bf16 = ld_b; e.out_f32 = out_f; e.ld_f32 = ld_f;
         } else {
             e.res = res; e.ld_res = ld_res;
             e.gamma = ln ? ln->g : nullptr; e.beta = ln ? ln->b : nullptr;
@@ -756,6 +881,8 @@ struct vb200_engine {
             l.ln_g = ln->g; l.ln_b = ln->b; l.ln_out_f = out_f; l.ln_out_h = out_b; l.ln_ld = W.N;
             l.ld_out = out_f ? ld_f : 0; l.ld_a = out_b ? ld_b * S : 0;
             l.ln_M = static_cast<int>(a_rows); l.ln_N = W.N;
+            if (fa != nullptr && fa->res_stats != nullptr)
+                l.ln_pend = vb::LnPending{fa->res_stats, fa->res_parts, fa->stats_ld, fa->res_ln->g, fa->res_ln->b};
             pl.ops.push_back(l);
         }
     }
@@ -849,33 +976,82 @@ struct vb200_engine {
         };
         auto qkv_at = [&](const uint8_t* q, int col) -> const void* { return q + static_cast<size_t>(col) * qe; };
 
-        // ---- image embedding: LayerNorm(feat.W_img^T + loc.W_loc^T + b) as ONE GEMM over K = v_feat + 64
-        if (do_v)
-            add_linear(pl, pl.img_a, Mv, pl.kp, img_emb, vb::kActNone, nullptr, 0, &vemb_ln, pl.v_b16[0], Hv, pl.v_f32[0], Hv,
-                       1);           // side stream: overlaps the text layers that precede the first co-attention
-        int tc = 0, vc = 0;
+        // ---- LayerNorm fold state of the two streams: `pend` = the LayerNorm still to be applied to buffers [cur] (null: the
+        // buffers hold final values), its row statistics live in stats[cur]
+        struct StreamSt {
+            float** f32; bf16** b16; float2** stats; int cur; const LNW* pend; int hid, rows, stats_ld, stream; const float* mask; int seq;
+            uint8_t* qkv; bf16* ctx; bf16* inter;
+        };
+        if (ln_fold) {
+            pl.stats_ld_t = (Mt + 31) & ~31; pl.stats_ld_v = (Mv + 31) & ~31;
+            for (int i = 0; i < 2; ++i) {
+                pl.t_stats[i] = static_cast<float2*>(pl.mem.alloc(static_cast<size_t>(H / 32) * pl.stats_ld_t * sizeof(float2)));
+                pl.v_stats[i] = static_cast<float2*>(pl.mem.alloc(static_cast<size_t>(Hv / 32) * pl.stats_ld_v * sizeof(float2)));
+            }
+        }
+        StreamSt ts{pl.t_f32, pl.t_b16, pl.t_stats, 0, nullptr, H, Mt, pl.stats_ld_t, 0, pl.mask_t, T, qkv_t, ctx_t, inter_t};
+        StreamSt vs{pl.v_f32, pl.v_b16, pl.v_stats, 0, nullptr, Hv, Mv, pl.stats_ld_v, 1, pl.mask_v, V, qkv_v, ctx_v, inter_v};
+        auto fold_in_args = [&](const StreamSt& st, int which) {          // consume buffers[which] of a stream as a GEMM's A operand
+            FoldArgs fa;
+            fa.a_stats = st.stats[which]; fa.a_parts = st.hid / 32; fa.stats_ld = st.stats_ld;
+            return fa;
+        };
+        // GEMM + LayerNorm whose residual is buffers[rwhich] of stream st (its own LayerNorm possibly pending: res_pend);
+        // the result lands in buffers[owhich]; keep == true leaves THIS LayerNorm pending (statistics in stats[owhich])
+        auto ln_linear = [&](StreamSt& st, const bf16* A, int64_t lda, const LinearW& W, const LNW& ln, int rwhich, const LNW* res_pend,
+                             int owhich, bool keep, Op::Sync sync) {
+            FoldArgs fa;
+            fa.stats_ld = st.stats_ld;
+            if (res_pend != nullptr) { fa.res_stats = st.stats[rwhich]; fa.res_parts = st.hid / 32; fa.res_ln = res_pend; }
+            if (keep) fa.out_stats = st.stats[owhich];
+            add_linear(pl, A, st.rows, lda, W, vb::kActNone, st.f32[rwhich], st.hid, &ln, st.b16[owhich], st.hid, st.f32[owhich], st.hid,
+                       st.stream, sync, nullptr, 0, (res_pend != nullptr || keep) ? &fa : nullptr);
+        };
 
-        auto single_layer = [&](const LayerW& L, int M, int hid, int inter, int heads, float** f32, bf16** b16, int& cur,
-                                uint8_t* qkv, bf16* ctx, bf16* inter_buf, const float* mask, int seq, int stream) {
+        // ---- image embedding: LayerNorm(feat.W_img^T + loc.W_loc^T + b) as ONE GEMM over K = v_feat + 64
+        if (do_v) {
+            const bool keep = ln_fold && fold_out_v.count("E") != 0;
+            FoldArgs fa;
+            fa.stats_ld = vs.stats_ld;
+            if (keep) fa.out_stats = vs.stats[0];
+            add_linear(pl, pl.img_a, Mv, pl.kp, img_emb, vb::kActNone, nullptr, 0, &vemb_ln, pl.v_b16[0], Hv, pl.v_f32[0], Hv,
+                       1, Op::NONE, nullptr, 0, keep ? &fa : nullptr);   // side stream: overlaps the text layers ahead of the first co-attention
+        }
+        if (do_v && ln_fold && fold_out_v.count("E") != 0) vs.pend = &vemb_ln;
+
+        // one BertLayer / BertImageLayer.  keep_out: this stage's output LayerNorm stays pending (LayerNorm fold map, ingest())
+        auto single_layer = [&](const LayerW& L, StreamSt& st, int inter, int heads, bool keep_out) {
+            const int hid = st.hid, cur = st.cur, M = st.rows, stream = st.stream;
             bf16* qb; float* qf;
-            qkv_out(qkv, qb, qf);
-            add_linear(pl, b16[cur], M, hid, L.qkv, vb::kActNone, nullptr, 0, nullptr, qb, 3 * hid, qf, 3 * hid, stream);
+            qkv_out(st.qkv, qb, qf);
+            {
+                FoldArgs fa = fold_in_args(st, cur);
+                add_linear(pl, st.b16[cur], M, hid, L.qkv, vb::kActNone, nullptr, 0, nullptr, qb, 3 * hid, qf, 3 * hid, stream, Op::NONE,
+                           nullptr, 0, st.pend ? &fa : nullptr);
+            }
             if (!x3) {
                 Op a{};
                 a.kind = Op::SELF_ATTN;
                 a.stream = stream;
-                a.qkv_a = qb; a.ld_a = 3 * hid; a.hidden = hid; a.mask_a = mask; a.ctx_a = ctx; a.ld_ctx_a = hid;
-                a.B = B; a.La = seq; a.heads = heads; a.head_dim = hid / heads;
-                a.flops = 4.0 * B * heads * seq * seq * (hid / heads);
+                a.qkv_a = qb; a.ld_a = 3 * hid; a.hidden = hid; a.mask_a = st.mask; a.ctx_a = st.ctx; a.ld_ctx_a = hid;
+                a.B = B; a.La = st.seq; a.heads = heads; a.head_dim = hid / heads;
+                a.flops = 4.0 * B * heads * st.seq * st.seq * (hid / heads);
                 pl.flops += a.flops;
                 ops.push_back(a);
             }
             if (x3 || want_attn)
-                add_attn_f32(pl, qkv_at(qkv, 0), 3 * hid, qkv_at(qkv, hid), qkv_at(qkv, 2 * hid), 3 * hid, mask, seq, seq, heads, hid,
-                             ctx, want_attn, stream);
-            add_linear(pl, ctx, M, hid, L.attn_out, vb::kActNone, f32[cur], hid, &L.ln1, b16[1 - cur], hid, f32[1 - cur], hid, stream);
-            add_linear(pl, b16[1 - cur], M, hid, L.inter, vb::kActGelu, nullptr, 0, nullptr, inter_buf, inter, nullptr, 0, stream);
-            add_linear(pl, inter_buf, M, inter, L.out, vb::kActNone, f32[1 - cur], hid, &L.ln2, b16[cur], hid, f32[cur], hid, stream);
+                add_attn_f32(pl, qkv_at(st.qkv, 0), 3 * hid, qkv_at(st.qkv, hid), qkv_at(st.qkv, 2 * hid), 3 * hid, st.mask, st.seq, st.seq,
+                             heads, hid, st.ctx, want_attn, stream);
+            // attention output + LayerNorm1 (residual: the layer input) -> buffers [1 - cur]
+            ln_linear(st, st.ctx, hid, L.attn_out, L.ln1, cur, st.pend, 1 - cur, ln_fold, Op::NONE);
+            {
+                FoldArgs fa = fold_in_args(st, 1 - cur);
+                add_linear(pl, st.b16[1 - cur], M, hid, L.inter, vb::kActGelu, nullptr, 0, nullptr, st.inter, inter, nullptr, 0, stream,
+                           Op::NONE, nullptr, 0, ln_fold ? &fa : nullptr);
+            }
+            // FFN output + LayerNorm2 (residual: LayerNorm1's output) -> buffers [cur]
+            ln_linear(st, st.inter, inter, L.out, L.ln2, 1 - cur, ln_fold ? &L.ln1 : nullptr, cur, keep_out, Op::NONE);
+            st.pend = keep_out ? &L.ln2 : nullptr;
         };
 
         bool in_suffix = false;
@@ -883,18 +1059,22 @@ struct vb200_engine {
             const int idx = atoi(step.c_str() + 1);
             if (step[0] == 'C') in_suffix = true;
             if (step[0] == 'T') {
-                if (in_suffix ? do_s : do_t)
-                    single_layer(t_layers[idx], Mt, H, c.inter, c.heads, pl.t_f32, pl.t_b16, tc, qkv_t, ctx_t, inter_t, pl.mask_t, T, 0);
+                if (in_suffix ? do_s : do_t) single_layer(t_layers[idx], ts, c.inter, c.heads, ln_fold && fold_out_t.count(step) != 0);
             } else if (step[0] == 'V') {
-                if (in_suffix ? do_s : do_v)
-                    single_layer(v_layers[idx], Mv, Hv, c.v_inter, c.v_heads, pl.v_f32, pl.v_b16, vc, qkv_v, ctx_v, inter_v, pl.mask_v, V, 1);
+                if (in_suffix ? do_s : do_v) single_layer(v_layers[idx], vs, c.v_inter, c.v_heads, ln_fold && fold_out_v.count(step) != 0);
             } else if (do_s) {
                 const ConnW& W = c_layers[idx];
+                const int tcur = ts.cur, vcur = vs.cur;
                 bf16 *qvb, *qtb; float *qvf, *qtf;
                 qkv_out(qkv_v, qvb, qvf);
                 qkv_out(qkv_t, qtb, qtf);
-                add_linear(pl, pl.v_b16[vc], Mv, Hv, W.qkv_img, vb::kActNone, nullptr, 0, nullptr, qvb, 3 * Hb, qvf, 3 * Hb, 1);
-                add_linear(pl, pl.t_b16[tc], Mt, H, W.qkv_txt, vb::kActNone, nullptr, 0, nullptr, qtb, 3 * Hb, qtf, 3 * Hb, 0);
+                {
+                    FoldArgs fv = fold_in_args(vs, vcur), ft = fold_in_args(ts, tcur);
+                    add_linear(pl, pl.v_b16[vcur], Mv, Hv, W.qkv_img, vb::kActNone, nullptr, 0, nullptr, qvb, 3 * Hb, qvf, 3 * Hb, 1, Op::NONE,
+                               nullptr, 0, vs.pend ? &fv : nullptr);
+                    add_linear(pl, pl.t_b16[tcur], Mt, H, W.qkv_txt, vb::kActNone, nullptr, 0, nullptr, qtb, 3 * Hb, qtf, 3 * Hb, 0, Op::NONE,
+                               nullptr, 0, ts.pend ? &ft : nullptr);
+                }
                 const size_t first_co = ops.size();
                 if (!x3) {
                     Op a{};
@@ -914,16 +1094,30 @@ struct vb200_engine {
                                  c.bi_heads, Hb, ctx_v, want_attn, 0);
                 }
                 ops[first_co].sync = Op::JOIN;              // needs both projections
-                // image branch (side stream; forks from the co-attention)
-                add_linear(pl, ctx_v, Mv, Hb, W.dense1, vb::kActNone, pl.v_f32[vc], Hv, &W.ln1, pl.v_b16[1 - vc], Hv, pl.v_f32[1 - vc], Hv, 1, Op::FORK);
-                add_linear(pl, pl.v_b16[1 - vc], Mv, Hv, W.v_inter, vb::kActGelu, nullptr, 0, nullptr, inter_v, c.v_inter, nullptr, 0, 1);
-                add_linear(pl, inter_v, Mv, c.v_inter, W.v_out, vb::kActNone, pl.v_f32[1 - vc], Hv, &W.v_ln, pl.v_b16[vc], Hv, pl.v_f32[vc], Hv, 1);
+                const bool keep_v = ln_fold && fold_out_v.count(step) != 0, keep_t = ln_fold && fold_out_t.count(step) != 0;
+                // image branch (side stream; forks from the co-attention): biOutput.dense1 + LayerNorm1, v_intermediate, v_output + LayerNorm
+                ln_linear(vs, ctx_v, Hb, W.dense1, W.ln1, vcur, vs.pend, 1 - vcur, ln_fold, Op::FORK);
+                {
+                    FoldArgs fa = fold_in_args(vs, 1 - vcur);
+                    add_linear(pl, pl.v_b16[1 - vcur], Mv, Hv, W.v_inter, vb::kActGelu, nullptr, 0, nullptr, inter_v, c.v_inter, nullptr, 0, 1,
+                               Op::NONE, nullptr, 0, ln_fold ? &fa : nullptr);
+                }
+                ln_linear(vs, inter_v, c.v_inter, W.v_out, W.v_ln, 1 - vcur, ln_fold ? &W.ln1 : nullptr, vcur, keep_v, Op::NONE);
+                vs.pend = keep_v ? &W.v_ln : nullptr;
                 // text branch (main stream)
-                add_linear(pl, ctx_t, Mt, Hb, W.dense2, vb::kActNone, pl.t_f32[tc], H, &W.ln2, pl.t_b16[1 - tc], H, pl.t_f32[1 - tc], H, 0);
-                add_linear(pl, pl.t_b16[1 - tc], Mt, H, W.t_inter, vb::kActGelu, nullptr, 0, nullptr, inter_t, c.inter, nullptr, 0, 0);
-                add_linear(pl, inter_t, Mt, c.inter, W.t_out, vb::kActNone, pl.t_f32[1 - tc], H, &W.t_ln, pl.t_b16[tc], H, pl.t_f32[tc], H, 0);
+                ln_linear(ts, ctx_t, Hb, W.dense2, W.ln2, tcur, ts.pend, 1 - tcur, ln_fold, Op::NONE);
+                {
+                    FoldArgs fa = fold_in_args(ts, 1 - tcur);
+                    add_linear(pl, pl.t_b16[1 - tcur], Mt, H, W.t_inter, vb::kActGelu, nullptr, 0, nullptr, inter_t, c.inter, nullptr, 0, 0,
+                               Op::NONE, nullptr, 0, ln_fold ? &fa : nullptr);
+                }
+                ln_linear(ts, inter_t, c.inter, W.t_out, W.t_ln, 1 - tcur, ln_fold ? &W.ln2 : nullptr, tcur, keep_t, Op::NONE);
+                ts.pend = keep_t ? &W.t_ln : nullptr;
             }
         }
+        if ((do_s || do_t) && ts.pend != nullptr) fail(VB200_ERR_INVALID, "LayerNorm fold: the text stream ends with a pending LayerNorm");
+        if ((do_s || do_v) && vs.pend != nullptr) fail(VB200_ERR_INVALID, "LayerNorm fold: the image stream ends with a pending LayerNorm");
+        const int tc = ts.cur, vc = vs.cur;
         pl.t_cur = tc; pl.v_cur = vc;
         pl.outs[9] = OutBuf{pl.t_f32[tc], Mt, H, H};
         pl.outs[10] = OutBuf{pl.v_f32[vc], Mv, Hv, Hv};
@@ -1053,7 +1247,7 @@ struct vb200_engine {
             case Op::LAYERNORM:
                 CUDA_CHECK(vb::launch_ln_residual(op.ln_y, op.ln_ld, op.ln_res, op.ld_x, op.ln_g, op.ln_b, cfg.ln_eps, op.ln_out_f,
                                                   op.ld_out, op.ln_out_h, op.ld_a, op.ln_M, op.ln_N, opt.act_fp16, x3 ? 1 : 0,
-                                                  light_pdl(), st));
+                                                  light_pdl(), st, op.ln_pend.stats ? &op.ln_pend : nullptr));
                 break;
             case Op::ATTN_F32:
                 CUDA_CHECK(vb::launch_attention_f32(op.f_q, op.f_ld_q, op.f_k, op.f_v, op.f_ld_kv, op.f_in, op.f_mask, op.B, op.f_Lq,
@@ -1324,7 +1518,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         Config c = parse_config(config_json);
         {   // audit the state_dict (names, shapes, dtypes, strictness) before touching any device
             vb200_engine audit;
-            audit.cfg = c; audit.opt = o; audit.dry = true; audit.x3 = o.split_fp32 != 0;
+            audit.cfg = c; audit.opt = o; audit.dry = true; audit.x3 = o.split_fp32 != 0; audit.ln_fold = false;
             audit.ingest(n_tensors, tensors);
         }
         require_device(o.device);
@@ -1334,6 +1528,9 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->x3 = o.split_fp32 != 0;
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
+        eng->ln_fold = o.ln_fold >= 0;
+        if (const char* v = getenv("VB200_LNFOLD")) eng->ln_fold = (strcmp(v, "0") != 0);
+        if (eng->x3 || eng->fused_ln) eng->ln_fold = false;      // those modes keep every LayerNorm as its own step
         eng->max_plans = o.max_plans > 0 ? static_cast<size_t>(o.max_plans) : 24;
         if (const char* v = getenv("VB200_MAX_PLANS")) { const int n = atoi(v); if (n > 0) eng->max_plans = static_cast<size_t>(n); }
         eng->pdl_light = eng->pdl_medium = false;
@@ -1537,7 +1734,8 @@ int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n
                 dims[4 * i + 0] = op.kind == Op::GEMM ? op.ep.M : (op.kind == Op::LAYERNORM ? op.ln_M : op.B);
                 dims[4 * i + 1] = op.kind == Op::GEMM ? op.ep.N : (op.kind == Op::LAYERNORM ? op.ln_N : op.La);
                 dims[4 * i + 2] = op.kind == Op::GEMM ? op.ep.K : op.Lb;
-                dims[4 * i + 3] = op.kind == Op::GEMM ? (op.ep.act | (op.ln ? 16 : 0)) : op.heads;
+                dims[4 * i + 3] = op.kind == Op::GEMM ? (op.ep.act | (op.ln ? 16 : 0) | (op.ep.ln_mode == 4 ? 32 : 0) | (op.ep.ln_mode == 5 ? 64 : 0))
+                                                      : op.heads;
             }
         }
     });
@@ -1555,6 +1753,7 @@ int vb200_model_dim(vb200_handle h, const char* key, int64_t* value) {
         else if (k == "task_specific_tokens") *value = c.task_tokens;
         else if (k == "weight_bytes") *value = static_cast<int64_t>(h->weights.total);
         else if (k == "operand_width_factor") *value = h->x3 ? 3 : 1;
+        else if (k == "ln_fold") *value = h->ln_fold ? 1 : 0;
         else if (k == "n_plans") *value = static_cast<int64_t>(h->plans.size());
         else if (k == "n_layers_scheduled") *value = static_cast<int64_t>(h->schedule.size());
         else fail(VB200_ERR_INVALID, "unknown model dimension \"%s\"", key);
@@ -1626,6 +1825,25 @@ int vb200_linear_split(const void* x16, int64_t ld_x, const void* w16, int64_t l
         e.ld_bf16 = (int)ld_y16; e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32; e.act = act; e.a_f16 = 1; e.out_f16 = 1;
         e.split16 = y16 != nullptr ? 1 : 0;
         CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, false, static_cast<cudaStream_t>(cuda_stream)));
+    });
+}
+
+int vb200_linear_ln(const void* x16, int64_t ld_x, const void* w16, int64_t ld_w, const float* bias, int32_t mode, const void* a_stats,
+                    int32_t a_parts, const float* fold_s, const float* res, int64_t ld_res, const void* res_stats, int32_t res_parts,
+                    const float* res_gamma, const float* res_beta, void* out_stats, int32_t stats_ld, float eps, int32_t act, void* y16,
+                    int64_t ld_y16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K, int32_t act_fp16, void* cuda_stream) {
+    return op_guard([&] {
+        if (mode != 4 && mode != 5) fail(VB200_ERR_INVALID, "vb200_linear_ln: mode must be 4 (fold-in) or 5 (pre-LayerNorm output)");
+        CUtensorMap ta = make_tmap(x16, M, K, ld_x, 128, act_fp16 != 0);
+        CUtensorMap tb = make_tmap(w16, N, K, ld_w, 128, act_fp16 != 0);
+        GemmEpilogue e{};
+        e.M = (int)M; e.N = (int)N; e.K = (int)K; e.bias = bias; e.eps = eps; e.act = act; e.a_f16 = act_fp16 ? 1 : 0; e.out_f16 = e.a_f16;
+        e.out_bf16 = static_cast<bf16*>(y16); e.ld_bf16 = (int)ld_y16; e.out_f32 = y_f32; e.ld_f32 = (int)ld_y_f32;
+        e.ln_mode = mode; e.stats_ld = stats_ld;
+        e.a_stats = static_cast<const float2*>(a_stats); e.a_parts = a_parts; e.fold_s = fold_s;
+        e.res = res; e.ld_res = (int)ld_res; e.res_stats = static_cast<const float2*>(res_stats); e.res_parts = res_parts;
+        e.res_gamma = res_gamma; e.res_beta = res_beta; e.out_stats = static_cast<float2*>(out_stats);
+        CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, 128, false, static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 

@@ -33,7 +33,8 @@ constexpr int kUmmaK = 16;
 // EPI8: eight epilogue warps (two column groups per TMEM lane quarter) -- every instantiation uses it now (KCfg); with four,
 // each SM sub-partition ran ONE epilogue warp and every dependent instruction paid its full latency.
 // MODE 0: default.  MODE 3: the same kernel with the fp32-parity mode's hi | lo | hi 16-bit output (a compile-time variant so the
-// default kernel's 96-register budget is untouched).  MODE 2 ("WIDE2", BLOCK_N = 256 only):
+// default kernel's 96-register budget is untouched).  MODE 4 / 5: the LayerNorm fold (see row_stats below) -- 4 ("FOLD") consumes an
+// activation whose LayerNorm is still pending, 5 ("LNOUT") produces one.  MODE 2 ("WIDE2", BLOCK_N = 256 only):
 // 128x256 tiles at TWO CTAs per SM -- a 256-wide MMA takes 128 cycles, so the one-issuer limit (134 cycles per MMA) does not
 // bite, and two CTAs keep both the tensor pipe and the ~98 B/clk operand ingest busy; paid for with a 2-stage 48 KB ring, a
 // single-buffered 256-column accumulator and the bias read through L1 instead of shared memory (the budget is 96 bytes short).
@@ -321,6 +322,32 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
     __syncwarp();
 }
 
+// ---- LayerNorm folded into the GEMMs around it (round 2; replaces 58 of the 62 row-LayerNorm launches of a forward)
+// A residual block ends in  a = LayerNorm_{g,b}(u),  u = dense(x) + residual.  Instead of materialising `a`, the producing GEMM
+// (MODE 5) writes u -- fp32 for the residual stream, 16-bit as the next GEMM's operand -- plus, per row and 32-column chunk, the
+// pair (mean, M2 = sum (x - mean)^2).  Whoever needs `a` later rebuilds it from exact per-row statistics:
+//   * a GEMM that consumes `a` as its A operand (MODE 4) runs on u with column-scaled weights W' = g o W and finishes with
+//         y[m, n] = rstd_m * (acc[m, n] - mean_m * s_n) + c_n,     s_n = sum_k W'[n, k],  c_n = sum_k b_k W[n, k] + bias_n
+//     (algebraically LayerNorm(u) W^T + bias; s is summed over the ROUNDED 16-bit W' the tensor cores see, so the mean term
+//     cancels exactly);
+//   * a GEMM (MODE 5) or the row-LayerNorm kernel that needs `a` as its residual computes (u - mean) rstd g + b on the fly.
+// The chunk statistics are combined with Chan's parallel formula (equal counts), deterministically and per row only, so a
+// pair's result still does not depend on its batch neighbours (bit-exact sharding).  stats layout: [N / 32][ld] float2, part-major
+// (a warp's 32 rows are 256 contiguous bytes).
+__device__ __forceinline__ void row_stats(const float2* __restrict__ stats, int parts, int ld, int m, float n_cols, float eps,
+                                          float& mean, float& rstd) {
+    float sm = 0.0f;
+    for (int q = 0; q < parts; ++q) sm += stats[static_cast<size_t>(q) * ld + m].x;
+    mean = sm / static_cast<float>(parts);
+    float m2 = 0.0f;
+    for (int q = 0; q < parts; ++q) {
+        const float2 t = stats[static_cast<size_t>(q) * ld + m];
+        const float d = t.x - mean;
+        m2 += t.y + 32.0f * d * d;
+    }
+    rstd = 1.0f / sqrtf(m2 / n_cols + eps);
+}
+
 template <int BLOCK_N, bool LN, int ACT, int MODE = 0>
 struct KCfg { using type = PCfg<BLOCK_N, LN, true, MODE>; };   // 8 epilogue warps everywhere: with 4, each SM sub-partition
                                                                  // runs ONE epilogue warp -- every dependent instruction pays
@@ -537,6 +564,16 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 } else {
                     bias_t = p.bias + n0;                  // WIDE2: straight from global / L1 (host guarantees bias != null, N % 256 == 0)
                 }
+                // LayerNorm fold: this row's statistics, computed while the main loop runs (the epilogue warps are idle until the
+                // accumulator is ready).  a_*: pending LayerNorm of the A operand (MODE 4); r_*: of the residual (MODE 5).
+                float a_mean = 0.0f, a_rstd = 1.0f, r_mean = 0.0f, r_rstd = 1.0f;
+                if constexpr (MODE == 4) {
+                    if (m_ok) row_stats(p.a_stats, p.a_parts, p.stats_ld, m, static_cast<float>(p.a_parts * 32), p.eps, a_mean, a_rstd);
+                }
+                if constexpr (MODE == 5) {
+                    if (m_ok && p.res_stats != nullptr)
+                        row_stats(p.res_stats, p.res_parts, p.stats_ld, m, static_cast<float>(p.res_parts * 32), p.eps, r_mean, r_rstd);
+                }
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (stamp) stamps[4] = clock64();
@@ -549,7 +586,48 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                      (p.tma_store == 1 ? (p.out_bf16 != nullptr && p.out_f32 == nullptr)
                                                        : (p.out_f32 != nullptr && p.out_bf16 == nullptr));
                 auto finish_chunk = [&](float (&v)[32], int nc) {
+                    if constexpr (MODE == 4) {                       // y = rstd * (acc - mean * s) + c; c arrives as the bias below
+                        const float4* s4 = reinterpret_cast<const float4*>(p.fold_s + nc);
+                        const float ms = -a_mean * a_rstd;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 sv = (nc + 4 * j < p.N) ? __ldg(s4 + j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            v[4 * j] = fmaf(v[4 * j], a_rstd, ms * sv.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a_rstd, ms * sv.y);
+                            v[4 * j + 2] = fmaf(v[4 * j + 2], a_rstd, ms * sv.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a_rstd, ms * sv.w);
+                        }
+                    }
                     bias_act32<ACT>(v, bias_t + (nc - n0));
+                    if constexpr (MODE == 5) {
+                        // u = acc + bias + residual (the residual's own LayerNorm applied on the fly when it is still pending),
+                        // then this chunk's (mean, M2) for whoever consumes LayerNorm(u)
+                        if (p.res != nullptr && m_ok) {
+                            const float4* rp = reinterpret_cast<const float4*>(p.res + static_cast<size_t>(m) * p.ld_res + nc);
+                            if (p.res_stats != nullptr) {
+                                const float4* g4 = reinterpret_cast<const float4*>(p.res_gamma + nc);
+                                const float4* b4 = reinterpret_cast<const float4*>(p.res_beta + nc);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 r = rp[j], g = __ldg(g4 + j), b = __ldg(b4 + j);
+                                    v[4 * j] += fmaf((r.x - r_mean) * r_rstd, g.x, b.x); v[4 * j + 1] += fmaf((r.y - r_mean) * r_rstd, g.y, b.y);
+                                    v[4 * j + 2] += fmaf((r.z - r_mean) * r_rstd, g.z, b.z); v[4 * j + 3] += fmaf((r.w - r_mean) * r_rstd, g.w, b.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 r = rp[j];
+                                    v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                                }
+                            }
+                        }
+                        float cs = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cs += v[j];
+                        const float cm = cs * (1.0f / 32.0f);
+                        float m2 = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { const float d = v[j] - cm; m2 = fmaf(d, d, m2); }
+                        if (m_ok) p.out_stats[static_cast<size_t>(nc >> 5) * p.stats_ld + m] = make_float2(cm, m2);
+                    }
                     if ((p.debug & 2) && __float_as_uint(v[0]) != 0x7fc12345u) return;     // timing decomposition: no stores
                     if (p.mul != nullptr && m_ok) {
                         const float* mp = p.mul + static_cast<size_t>(m) * p.ld_mul + nc;

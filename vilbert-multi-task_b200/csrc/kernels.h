@@ -35,6 +35,17 @@ struct GemmEpilogue {
     const void* tmap_c_host;      // host pointer to the CUtensorMap of the output (launchers copy it into a kernel parameter)
     int tma_store;                // 0: register/LSU stores only; 1: 16-bit output, 2: fp32 output may leave through a TMA store
                                   // (plain persistent kernel: the LAST tile of every CTA is staged in the idle operand ring)
+    // LayerNorm fold (gemm_persistent.cuh, PCfg MODE 4 / 5).  stats arrays: [N_src / 32][stats_ld] float2 (mean, M2) per 32 columns
+    const float2* a_stats;        // MODE 4: statistics of the A operand's rows (its LayerNorm is pending); bias then holds c
+    int a_parts;                  //         N_src / 32
+    const float* fold_s;          //         s_n = sum_k W'[n, k]   [N]
+    const float2* res_stats;      // MODE 5: statistics of the residual's rows, or null when the residual holds final values
+    int res_parts;
+    const float* res_gamma;       //         the residual's pending LayerNorm parameters [N]
+    const float* res_beta;
+    float2* out_stats;            // MODE 5: this GEMM's own row statistics, [N / 32][stats_ld]
+    int stats_ld;                 // row capacity of every stats array of this launch (>= M)
+    int ln_mode;                  // 0 none, 4 fold-in (consumer), 5 pre-LayerNorm output + statistics (producer)
     int debug;                    // timing decomposition only (VB200_DEBUG through vb200_linear): 1 = issue no MMA, 2 = no epilogue
                                   // stores, 4 = no operand loads (the ring is "filled" by plain arrives); results are garbage
 };                                //   every GEMM starts on HBM misses (weights never survive in the 126 MB L2 until the next step)
@@ -64,9 +75,14 @@ cudaError_t launch_co_attention(const __nv_bfloat16* qkv_img, int ld_img, const 
                                 int T, int V, int heads, int head_dim, int pdl, int f16, cudaStream_t st);
 
 // un-fused LayerNorm(y + res): fp32 stream out + 16-bit operand out (layernorm.cu); split16: hi | lo | hi operand (fp32-parity mode)
+struct LnPending {                // a residual whose own LayerNorm is still pending (LayerNorm fold): statistics + parameters
+    const float2* stats;          // [parts][ld] (mean, M2) per 32 columns
+    int parts, ld;
+    const float *gamma, *beta;
+};
 cudaError_t launch_ln_residual(const float* y, int ld_y, const float* res, int ld_res, const float* gamma, const float* beta,
                                float eps, float* out_f32, int ld_f32, __nv_bfloat16* out16, int ld16, int M, int N, int f16,
-                               int split16, int pdl, cudaStream_t st);
+                               int split16, int pdl, cudaStream_t st, const LnPending* res_pending = nullptr);
 // K2: word + position + token-type gather, task-token row at index 1, LayerNorm; also builds the additive text mask.
 cudaError_t launch_text_embed(const int64_t* ids, const int64_t* seg, const int64_t* input_mask, const int64_t* task,
                               const float* word, const float* pos, const float* type, const float* task_tab,
