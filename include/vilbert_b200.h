@@ -134,7 +134,7 @@ typedef struct {
                                       u = dense(x) + residual writes u (fp32 + 16-bit) and per-row (mean, M2) statistics instead of
                                       LayerNorm(u); the next GEMM runs on u with weights pre-scaled by gamma and finishes with
                                       rstd * (acc - mean * s) + c; residual readers rebuild LayerNorm(u) on the fly.  Same math,
-                                      58 of a forward's 62 LayerNorm launches gone.  Off in split_fp32 / fused_layernorm modes. */
+                                      57 of a forward's 62 LayerNorm launches gone.  Off in split_fp32 / fused_layernorm modes. */
     int32_t max_plans;             /* plan-cache bound: plans (workspace + CUDA graph per (batch, tokens, regions, select, slot))
                                       beyond this are evicted least-recently-used; 0 -> 24 */
 } vb200_options;

@@ -322,7 +322,7 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
     __syncwarp();
 }
 
-// ---- LayerNorm folded into the GEMMs around it (round 2; replaces 58 of the 62 row-LayerNorm launches of a forward)
+// ---- LayerNorm folded into the GEMMs around it (round 2; replaces 57 of the 62 row-LayerNorm launches of a forward)
 // A residual block ends in  a = LayerNorm_{g,b}(u),  u = dense(x) + residual.  Instead of materialising `a`, the producing GEMM
 // (MODE 5) writes u -- fp32 for the residual stream, 16-bit as the next GEMM's operand -- plus, per row and 32-column chunk, the
 // pair (mean, M2 = sum (x - mean)^2).  Whoever needs `a` later rebuilds it from exact per-row statistics:
