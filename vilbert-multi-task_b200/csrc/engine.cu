@@ -20,6 +20,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges per layer / per forward for nsys and ncu --nvtx
+
 #include "kernels.h"
 
 namespace {
@@ -359,6 +361,7 @@ struct Op {
     // fork/join markers for the two-stream graph
     enum Sync { NONE, FORK, JOIN } sync = NONE;
     double flops = 0;
+    const char* tag = nullptr;     // layer this launch belongs to ("T3", "V0", "C2", "embed", "heads"): NVTX range name
 };
 
 struct OutBuf { float* p = nullptr; int rows = 0, cols = 0, ld = 0; };
@@ -835,7 +838,7 @@ struct vb200_engine {
         op.kind = Op::GEMM;
         op.stream = stream;
         op.sync = sync;
-        op.ln = ln != nullptr && !split_ln;
+        op.ln = ln != nullptr && !split_ln && !keep_pending;      // cluster-LayerNorm epilogue (fused_layernorm option)
         op.block_n = vb::gemm_p_pick_block_n(W.N, op.ln);
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
         if (!x3 && !op.ln && !keep_pending && !fold_in && a_rows >= 256) {
@@ -1054,10 +1057,17 @@ struct vb200_engine {
             st.pend = keep_out ? &L.ln2 : nullptr;
         };
 
+        for (Op& op : ops) op.tag = "embed";
         bool in_suffix = false;
+        size_t tagged = ops.size();
         for (const std::string& step : schedule) {
+            for (; tagged < ops.size(); ++tagged) if (ops[tagged].tag == nullptr) ops[tagged].tag = "?";
             const int idx = atoi(step.c_str() + 1);
             if (step[0] == 'C') in_suffix = true;
+            struct Tagger {          // names the launches this step appends after its layer (engine.schedule outlives every plan)
+                std::vector<Op>& ops; size_t from; const char* name;
+                ~Tagger() { for (size_t i = from; i < ops.size(); ++i) ops[i].tag = name; }
+            } tagger{ops, ops.size(), step.c_str()};
             if (step[0] == 'T') {
                 if (in_suffix ? do_s : do_t) single_layer(t_layers[idx], ts, c.inter, c.heads, ln_fold && fold_out_t.count(step) != 0);
             } else if (step[0] == 'V') {
@@ -1122,7 +1132,9 @@ struct vb200_engine {
         pl.outs[9] = OutBuf{pl.t_f32[tc], Mt, H, H};
         pl.outs[10] = OutBuf{pl.v_f32[vc], Mv, Hv, Hv};
 
+        const size_t n_before_heads = ops.size();
         if (do_s) build_heads(pl, select);
+        for (size_t i = n_before_heads; i < ops.size(); ++i) ops[i].tag = "heads";
         for (Op& op : ops) if (op.kind == Op::ROWDOT) pl.flops += op.flops;
 
         link_pdl(pl);
@@ -1232,7 +1244,10 @@ struct vb200_engine {
                 else {
                     GemmEpilogue e = op.ep;
                     e.tmap_c_host = e.tma_store ? &op.tc : nullptr;       // Op objects move when the list grows: bind here
-                    CUDA_CHECK(vb::launch_gemm_persistent(op.ta, op.tb, e, op.block_n, op.ln, st));
+                    const cudaError_t le = vb::launch_gemm_persistent(op.ta, op.tb, e, op.block_n, op.ln, st);
+                    if (le != cudaSuccess)
+                        fail(VB200_ERR_CUDA, "GEMM launch failed: %s (layer %s, M=%d N=%d K=%d act=%d block_n=%d cluster_ln=%d ln_mode=%d split16=%d tma_store=%d)",
+                             cudaGetErrorString(le), op.tag ? op.tag : "?", e.M, e.N, e.K, e.act, op.block_n, (int)op.ln, e.ln_mode, e.split16, e.tma_store);
                 }
                 break;
             case Op::SELF_ATTN:
@@ -1265,7 +1280,14 @@ struct vb200_engine {
     // so far; a main op marked JOIN waits for the side stream.  Under capture these become graph edges.
     void run_ops(Plan& pl, cudaStream_t st) {
         bool side_started = false, side_dirty = false;
+        const char* open_tag = nullptr;
+        struct RangeGuard { const char*& t; ~RangeGuard() { if (t) nvtxRangePop(); } } guard{open_tag};
         for (const Op& op : pl.ops) {
+            if (op.tag != open_tag) {              // one NVTX range per layer of the schedule (enqueue side)
+                if (open_tag) nvtxRangePop();
+                open_tag = op.tag;
+                if (open_tag) nvtxRangePushA(open_tag);
+            }
             if (op.stream == 1) {
                 if (!side_started || op.sync == Op::FORK) {
                     CUDA_CHECK(cudaEventRecord(ev_fork, st));
@@ -1380,6 +1402,8 @@ struct vb200_engine {
     }
     void run_plan(Plan& pl, cudaStream_t st) {
         if (pl.ops.empty()) return;
+        struct R { R(const Plan& p) { char b[96]; snprintf(b, sizeof(b), "vb200 forward B=%d T=%d V=%d", p.B, p.T, p.V); nvtxRangePushA(b); }
+                   ~R() { nvtxRangePop(); } } range(pl);
         if (pl.exec) CUDA_CHECK(cudaGraphLaunch(pl.exec, st));
         else run_ops(pl, st);
     }
