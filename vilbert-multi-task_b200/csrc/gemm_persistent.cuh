@@ -286,6 +286,31 @@ __device__ __forceinline__ void store_f32_sw(uint4* st, float* out, int ld, int 
     }
 }
 
+// The reverse of store_f32_sw: 32 rows x 32 fp32 columns of a row-major matrix -> one row per lane.  Every global load instruction
+// reads 8 rows x 64 contiguous bytes (a row-per-lane load would touch 32 lines per instruction); 16 columns per pass through the
+// same swizzled 2 KB buffer.  Rows >= M read as zero.
+__device__ __forceinline__ void load_f32_sw(uint4* st, const float* src, int ld, int m_warp, int M, int ncol, float (&r)[32], int lane) {
+    const int j = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int row = it * 8 + (lane >> 2);
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (m_warp + row < M) u = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(m_warp + row) * ld + ncol + 16 * h + 4 * j);
+            st[sw_unit(row, j)] = u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const uint4 u = st[sw_unit(lane, jj)];
+            const float4 f = *reinterpret_cast<const float4*>(&u);
+            r[16 * h + 4 * jj] = f.x; r[16 * h + 4 * jj + 1] = f.y; r[16 * h + 4 * jj + 2] = f.z; r[16 * h + 4 * jj + 3] = f.w;
+        }
+        __syncwarp();
+    }
+}
+
 // LayerNorm outputs (fp32 stream copy and 16-bit GEMM operand) of one chunk from an fp32 [32][33] transpose buffer.
 template <bool F16>
 __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue& p, int m_warp, int ncol, const float (&v)[32],
@@ -336,14 +361,25 @@ __device__ __forceinline__ void store_ln_coalesced(float* st, const GemmEpilogue
 // (a warp's 32 rows are 256 contiguous bytes).
 __device__ __forceinline__ void row_stats(const float2* __restrict__ stats, int parts, int ld, int m, float n_cols, float eps,
                                           float& mean, float& rstd) {
+    // eight independent loads in flight per step (a rolled loop would pay one L2 round trip per chunk); the second pass re-reads
+    // the same lines from L1.  The summation order is fixed (q ascending), so results do not depend on anything but the row.
+    const float2* sp = stats + m;
     float sm = 0.0f;
-    for (int q = 0; q < parts; ++q) sm += stats[static_cast<size_t>(q) * ld + m].x;
+    for (int q0 = 0; q0 < parts; q0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (q0 + j < parts) ? sp[static_cast<size_t>(q0 + j) * ld].x : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm += t[j];
+    }
     mean = sm / static_cast<float>(parts);
     float m2 = 0.0f;
-    for (int q = 0; q < parts; ++q) {
-        const float2 t = stats[static_cast<size_t>(q) * ld + m];
-        const float d = t.x - mean;
-        m2 += t.y + 32.0f * d * d;
+    for (int q0 = 0; q0 < parts; q0 += 8) {
+        float2 t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (q0 + j < parts) ? sp[static_cast<size_t>(q0 + j) * ld] : make_float2(mean, 0.0f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = t[j].x - mean; m2 += t[j].y + 32.0f * d * d; }
     }
     rstd = 1.0f / sqrtf(m2 / n_cols + eps);
 }
@@ -428,7 +464,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             mbar_init(&ln_bar[a], LN ? cluster_size : 1u);                   // one arrival per CTA of the cluster
         }
         mbar_fence_init();
-        if (!LN && first_tile < total_tiles && p.pdl != 1 && !(p.debug & 4)) {
+#ifdef VB200_DECOMPOSE
+        const bool early_ok = !(p.debug & 4);
+#else
+        constexpr bool early_ok = true;
+#endif
+        if (!LN && first_tile < total_tiles && p.pdl != 1 && early_ok) {
             early_a = p.pdl != 5;
             const int m0 = (first_tile / num_n_tiles) * kBlockM, n0 = (first_tile % num_n_tiles) * BLOCK_N;
             early = min(kStages, num_kb);
@@ -476,9 +517,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         if (!early_a) tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
                     } else {
                         mbar_wait(&empty_bar[s], phase ^ 1u);
+#ifdef VB200_DECOMPOSE
                         if (p.debug & 4) {
                             mbar_arrive(&full_bar[s]);                 // timing decomposition: MMAs on stale shared memory
-                        } else {
+                        } else
+#endif
+                        {
                             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                             tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
                             tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, n0);
@@ -491,11 +535,15 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         __syncwarp();
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        // conv (VB200_DEBUG bit 8, experiment): the whole warp walks the loop converged and one elected lane issues, instead of
-        // lane 0 alone inside a divergent branch (where every tcgen05 instruction sits in an ELECT / BRA.U.ANY emulation loop).
-        const bool conv = (p.debug & 8) != 0;
-        if (conv || lane == 0) {
+        // This thread's serial loop (wait -> fence -> 4 x tcgen05.mma -> commit) is what paces a lone CTA: ~335 cycles per k-block
+        // with neither loads nor MMAs in it, ~530 with (profiles/r2_gemm_decomposition.md) -- every instruction here is on the
+        // critical path, so descriptors advance by adds and nothing optional lives inside the k loop.  (A converged warp with
+        // one elected issuing lane instead of lane 0 in a divergent branch measured 1-3 % -- not worth the extra syncs.)
+        if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f32acc(kBlockM, BLOCK_N, F16);
+            constexpr uint64_t kDescStage = static_cast<uint64_t>(Cfg::kStageBytes >> 4);       // descriptor address units (16 B)
+            const uint64_t da0 = umma_desc_kmajor_sw128(ring);
+            const uint64_t db0 = umma_desc_kmajor_sw128(ring + Cfg::kStageBytesA);
             int s = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -505,29 +553,36 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                uint32_t accumulate = 0u;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], phase);
                     tc_fence_after();
-                    if (stamps && it == 0 && kb == 0 && lane == 0) stamps[2] = clock64();
-                    uint8_t* sa = ring + s * Cfg::kStageBytes;
-                    const uint64_t da = umma_desc_kmajor_sw128(sa);
-                    const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
-                    if (conv ? elect_one() : true) {
-                        if (!(p.debug & 1)) {
+#ifdef VB200_STAMPS
+                    if (stamps && it == 0 && kb == 0) stamps[2] = clock64();
+#endif
+                    const uint64_t da = da0 + kDescStage * static_cast<uint64_t>(s);
+                    const uint64_t db = db0 + kDescStage * static_cast<uint64_t>(s);
+#ifdef VB200_DECOMPOSE
+                    if (!(p.debug & 1))
+#endif
+                    {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                                umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, accumulate);
+                            accumulate = 1u;
                         }
-                        umma_commit(&empty_bar[s]);
                     }
-                    if (conv) __syncwarp();
+                    umma_commit(&empty_bar[s]);
                     if (++s == kStages) { s = 0; phase ^= 1u; }
                 }
-                if (conv ? elect_one() : true) umma_commit(&tmem_full_bar[acc]);
-                if (conv) __syncwarp();
-                if (stamps && it == 0 && lane == 0) stamps[3] = clock64();
+                umma_commit(&tmem_full_bar[acc]);
+#ifdef VB200_STAMPS
+                if (stamps && it == 0) stamps[3] = clock64();
+#endif
             }
-            if (stamps && lane == 0) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
+#ifdef VB200_STAMPS
+            if (stamps) { stamps[10] = clock64(); stamps[11] = it; }     // steady state: (s10 - s2) / (tiles * k-blocks)
+#endif
             // This CTA's tensor work is issued: let the next kernel's CTAs come up while the epilogue drains (their
             // griddepcontrol.wait still holds them until this whole grid has finished).  Triggering at kernel entry instead made
             // the dependents sit on the second CTA slot of every SM for the whole main loop (measured: step 6 % slower).
@@ -600,23 +655,23 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     if constexpr (MODE == 5) {
                         // u = acc + bias + residual (the residual's own LayerNorm applied on the fly when it is still pending),
                         // then this chunk's (mean, M2) for whoever consumes LayerNorm(u)
-                        if (p.res != nullptr && m_ok) {
-                            const float4* rp = reinterpret_cast<const float4*>(p.res + static_cast<size_t>(m) * p.ld_res + nc);
+                        if (p.res != nullptr) {                         // warp-uniform
+                            float r[32];
+                            load_f32_sw(reinterpret_cast<uint4*>(s_xpose + ew * Cfg::kXposeBytesPerWarp), p.res, p.ld_res, m0 + q * 32, p.M,
+                                        nc, r, lane);
                             if (p.res_stats != nullptr) {
                                 const float4* g4 = reinterpret_cast<const float4*>(p.res_gamma + nc);
                                 const float4* b4 = reinterpret_cast<const float4*>(p.res_beta + nc);
+                                const float rs = r_rstd, rm = -r_mean * r_rstd;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    const float4 r = rp[j], g = __ldg(g4 + j), b = __ldg(b4 + j);
-                                    v[4 * j] += fmaf((r.x - r_mean) * r_rstd, g.x, b.x); v[4 * j + 1] += fmaf((r.y - r_mean) * r_rstd, g.y, b.y);
-                                    v[4 * j + 2] += fmaf((r.z - r_mean) * r_rstd, g.z, b.z); v[4 * j + 3] += fmaf((r.w - r_mean) * r_rstd, g.w, b.w);
+                                    const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+                                    v[4 * j] += fmaf(fmaf(r[4 * j], rs, rm), g.x, b.x); v[4 * j + 1] += fmaf(fmaf(r[4 * j + 1], rs, rm), g.y, b.y);
+                                    v[4 * j + 2] += fmaf(fmaf(r[4 * j + 2], rs, rm), g.z, b.z); v[4 * j + 3] += fmaf(fmaf(r[4 * j + 3], rs, rm), g.w, b.w);
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 r = rp[j];
-                                    v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-                                }
+                                for (int j = 0; j < 32; ++j) v[j] += r[j];
                             }
                         }
                         float cs = 0.0f;
@@ -628,7 +683,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         for (int j = 0; j < 32; ++j) { const float d = v[j] - cm; m2 = fmaf(d, d, m2); }
                         if (m_ok) p.out_stats[static_cast<size_t>(nc >> 5) * p.stats_ld + m] = make_float2(cm, m2);
                     }
+#ifdef VB200_DECOMPOSE
                     if ((p.debug & 2) && __float_as_uint(v[0]) != 0x7fc12345u) return;     // timing decomposition: no stores
+#endif
                     if (p.mul != nullptr && m_ok) {
                         const float* mp = p.mul + static_cast<size_t>(m) * p.ld_mul + nc;
                         if ((p.ld_mul & 3) == 0 && nc + 32 <= p.N) {          // 8 x 16-byte loads instead of 32 scalar ones
