@@ -130,11 +130,13 @@ typedef struct {
                                       fp32 accumulator; attention runs in fp32 on CUDA cores; GELU uses the 1.5e-7 erf.  3x the
                                       tensor work of the default mode -- for logit parity with the reference's fp32 forward
                                       (<= 1e-3 per logit, BASELINE.json north_star), not for throughput.  Implies act_fp16. */
-    int32_t ln_fold;               /* default on (-1: off): LayerNorm folded into the GEMMs around it.  The GEMM that produces
+    int32_t ln_fold;               /* 1: LayerNorm folded into the GEMMs around it (default off).  The GEMM that produces
                                       u = dense(x) + residual writes u (fp32 + 16-bit) and per-row (mean, M2) statistics instead of
                                       LayerNorm(u); the next GEMM runs on u with weights pre-scaled by gamma and finishes with
                                       rstd * (acc - mean * s) + c; residual readers rebuild LayerNorm(u) on the fly.  Same math,
-                                      57 of a forward's 62 LayerNorm launches gone.  Off in split_fp32 / fused_layernorm modes. */
+                                      57 of a forward's 62 LayerNorm launches gone -- but measured SLOWER on B200 at batch 64
+                                      (the extra epilogue work exceeds the row kernels it replaces, profiles/r2_ln_fold.md), so
+                                      it is an option, parity-tested, not the default.  Ignored in split_fp32 / fused_layernorm. */
     int32_t max_plans;             /* plan-cache bound: plans (workspace + CUDA graph per (batch, tokens, regions, select, slot))
                                       beyond this are evicted least-recently-used; 0 -> 24 */
 } vb200_options;

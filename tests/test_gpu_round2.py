@@ -364,7 +364,7 @@ def test_micro_batch_worker_on_engine(full_oracle, full_h):
 
 # ----------------------------------------------------------------------------------------------- LayerNorm fold
 def test_layernorm_fold_vs_unfolded_and_oracle(tiny_oracle, full_oracle, parity_log):
-    """Default engine (57 LayerNorms folded into the GEMMs around them) vs the round-1 form (every LayerNorm as GEMM + row kernel):
+    """ln_fold=True (57 LayerNorms folded into the GEMMs around them) vs the default form (every LayerNorm as GEMM + row kernel):
     both within the fp16 tolerance of the fp32 oracle, and the launch count of a forward drops accordingly."""
     from oracle import vilbert_ref as R
     from vilbert_b200 import _lib as L
@@ -372,7 +372,7 @@ def test_layernorm_fold_vs_unfolded_and_oracle(tiny_oracle, full_oracle, parity_
                              ("full", full_oracle, list(R.make_inputs(3, 30, 36, seed=92, pad_regions=2)))):
         ref = oracle(*inp, compute_pretraining_heads=True)
         dev = [t.cuda() for t in inp]
-        fold, plain = _engine(oracle), _engine(oracle, ln_fold=False)
+        fold, plain = _engine(oracle, ln_fold=True), _engine(oracle)
         a = fold(*dev, compute_pretraining_heads=True)
         b = plain(*dev, compute_pretraining_heads=True)
         torch.cuda.synchronize()

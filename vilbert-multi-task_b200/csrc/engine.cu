@@ -407,8 +407,10 @@ struct vb200_engine {
     vb200_options opt{};
     int num_labels = 0, gqa_labels = 0;
     bool dry = false;          // audit pass: check names / shapes / dtypes only, touch no device
-    bool ln_fold = true;       // LayerNorm folded into the neighbouring GEMMs (row_stats in gemm_persistent.cuh); VB200_LNFOLD=0 /
-                               // vb200_options::ln_fold = -1: every LayerNorm as GEMM (fp32 out) + row kernel, as in round 1
+    bool ln_fold = false;      // LayerNorm folded into the neighbouring GEMMs (row_stats in gemm_persistent.cuh); opt-in
+                               // (vb200_options::ln_fold = 1 / VB200_LNFOLD=1): 57 fewer launches per forward, but the heavier
+                               // GEMM epilogues cost more than the row kernels they replace (measured: 36.9 k vs 40.8 k pairs/s
+                               // at batch 64, profiles/r2_ln_fold.md) -- default stays GEMM (fp32 out) + row LayerNorm kernel
     std::set<std::string> fold_out_t, fold_out_v;   // stages ("T3", "C0", "E", ...) whose OUTPUT LayerNorm stays pending
     bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
@@ -1552,7 +1554,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->x3 = o.split_fp32 != 0;
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
-        eng->ln_fold = o.ln_fold >= 0;
+        eng->ln_fold = o.ln_fold > 0;
         if (const char* v = getenv("VB200_LNFOLD")) eng->ln_fold = (strcmp(v, "0") != 0);
         if (eng->x3 || eng->fused_ln) eng->ln_fold = false;      // those modes keep every LayerNorm as its own step
         eng->max_plans = o.max_plans > 0 ? static_cast<size_t>(o.max_plans) : 24;

@@ -47,7 +47,7 @@ class VILBertForVLTasks(object):
 
     def __init__(self, config: BertConfig, num_labels: int = 3129, state_dict=None, default_gpu: bool = True,
                  use_cuda_graph: bool = True, use_pdl: Optional[bool] = None, strict: bool = True, compute_dtype: str = "fp16",
-                 fused_layernorm: bool = False, return_attention: bool = False, max_plans: int = 0, ln_fold: bool = True):
+                 fused_layernorm: bool = False, return_attention: bool = False, max_plans: int = 0, ln_fold: bool = False):
         self.config = config
         self.num_labels = num_labels
         self._sd = _normalise_state_dict(state_dict) if state_dict is not None else None
@@ -150,7 +150,7 @@ class VILBertForVLTasks(object):
         opt.fused_layernorm = 1 if self._opts["fused_layernorm"] else 0
         opt.split_fp32 = 1 if self._opts["compute_dtype"] == "fp32x" else 0
         opt.max_plans = self._opts["max_plans"]
-        opt.ln_fold = 0 if self._opts["ln_fold"] else -1
+        opt.ln_fold = 1 if self._opts["ln_fold"] else 0
         h = C.c_void_p()
         with torch.cuda.device(device):
             rc = lib.vb200_create(self._config_json(), len(self._sd), arr, C.byref(opt), C.byref(h))
