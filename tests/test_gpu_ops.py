@@ -85,13 +85,16 @@ def _mk(M, N, K, seed=0, act=torch.bfloat16):
     (1984, 2304, 768, 128),     # text QKV at B=64
     (2304, 3072, 1024, 128),    # co-attention image QKV at B=64
     (1984, 3072, 768, 256),     # wide tile
+    (1984, 3072, 768, 192),     # 128x192 tiles (round 2): the N = 3072 GEMMs at batch 64 in one wave
+    (2304, 3072, 1024, 192),
+    (300, 384, 512, 192),       # ragged M, two N tiles
     (77, 64, 128, 64),          # narrow tile
     (64, 3129, 2048, 128),      # VQA logits: ragged N, M < tile
     (15872, 3072, 768, 128),    # B=512 text FFN-in: 2976 tiles, ~10 per persistent CTA
 ])
 @pytest.mark.parametrize("act_dt", ACT)
 def test_linear_bias(M, N, K, block_n, act_dt, variant, parity_log):
-    if variant == 2 and (block_n < 128 or N % block_n != 0):
+    if variant == 2 and (block_n not in (128, 256) or N % block_n != 0):
         pytest.skip("the CTA-pair kernel takes N that is a multiple of its 128/256-wide tile")
     x, w, b, _ = _mk(M, N, K, act=act_dt)
     ld = (N + 3) // 4 * 4
@@ -258,6 +261,20 @@ def test_layernorm_row_kernel(M, N, with_res, act_dt, parity_log):
 
 
 # ----------------------------------------------------------------------------------------------- round 2
+@pytest.mark.parametrize("act_dt", ACT)
+@pytest.mark.parametrize("act", [1, 2])
+def test_linear_act_192(act, act_dt, parity_log):
+    x, w, b, _ = _mk(1984, 3072, 768, seed=3, act=act_dt)
+    yb, yf = run_linear(x, w, b, act=act, block_n=192)
+    ref = ref_linear(x, w, b, act=act)
+    err = (yf - ref).abs().max().item()
+    parity_log(test="linear_act_192", act=act, max_abs_err=err)
+    assert err < 2e-3
+    assert (yb.float() - ref).abs().max().item() < 3e-2
+    _, y128 = run_linear(x, w, b, act=act, block_n=128)
+    assert torch.equal(yf, y128)                      # the tile width does not change a single bit
+
+
 def test_linear_gelu_outliers():
     """FFN pre-activations far from the origin (real checkpoints have outliers): GELU(-50) must be 0, not
     -1.1e-5 * x, and GELU(+50) must be x."""

@@ -412,6 +412,7 @@ struct vb200_engine {
                                // GEMM epilogues cost more than the row kernels they replace (measured: 36.9 k vs 40.8 k pairs/s
                                // at batch 64, profiles/r2_ln_fold.md) -- default stays GEMM (fp32 out) + row LayerNorm kernel
     std::set<std::string> fold_out_t, fold_out_v;   // stages ("T3", "C0", "E", ...) whose OUTPUT LayerNorm stays pending
+    bool wide192 = true;       // VB200_BN192=0: never pick the 128x192 tile (A/B)
     bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
@@ -847,6 +848,12 @@ struct vb200_engine {
             if (pair_bn > 0) op.pair = W.N % pair_bn == 0;
             else if (pair_bn < 0) op.pair = W.N % 256 == 0 && ((a_rows + 255) / 256) * (W.N / 256) >= 4 * (vb::num_sms_host() / 2);
             if (op.pair) op.block_n = pair_bn > 0 ? pair_bn : 256;
+        }
+        if (wide192 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && W.N % 192 == 0 && op.block_n == 128) {
+            // 128x192 tiles when 128-wide ones need more than one wave of the 2-per-SM CTA slots and 192-wide ones fit in one
+            // (the N = 3072 GEMMs at batch 64).  The tile width never changes an element's accumulation order: results are the same bits.
+            const long long slots = 2LL * vb::num_sms_host(), mt = (a_rows + 127) / 128;
+            if (mt * ((W.N + 127) / 128) > slots && mt * (W.N / 192) <= slots) op.block_n = 192;
         }
         op.ta = make_tmap(A, a_rows, static_cast<int64_t>(W.ldw) * S, lda * S, 128, opt.act_fp16 != 0);
         op.tb = make_tmap(W.w, W.N, static_cast<int64_t>(W.ldw) * S, static_cast<int64_t>(W.ldw) * S, op.pair ? op.block_n / 2 : op.block_n,
@@ -1554,6 +1561,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->x3 = o.split_fp32 != 0;
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
+        if (const char* v = getenv("VB200_BN192")) eng->wide192 = (strcmp(v, "0") != 0);
         eng->ln_fold = o.ln_fold > 0;
         if (const char* v = getenv("VB200_LNFOLD")) eng->ln_fold = (strcmp(v, "0") != 0);
         if (eng->x3 || eng->fused_ln) eng->ln_fold = false;      // those modes keep every LayerNorm as its own step

@@ -34,14 +34,17 @@ constexpr int kUmmaK = 16;
 // each SM sub-partition ran ONE epilogue warp and every dependent instruction paid its full latency.
 // MODE 0: default.  MODE 3: the same kernel with the fp32-parity mode's hi | lo | hi 16-bit output (a compile-time variant so the
 // default kernel's 96-register budget is untouched).  MODE 4 / 5: the LayerNorm fold (see row_stats below) -- 4 ("FOLD") consumes an
-// activation whose LayerNorm is still pending, 5 ("LNOUT") produces one.  MODE 2 ("WIDE2", BLOCK_N = 256 only):
+// activation whose LayerNorm is still pending, 5 ("LNOUT") produces one.  MODE 2 ("WIDE2", BLOCK_N = 192 or 256):
+// 128x192 is the default tile of the N = 3072 GEMMs at batch 64 (round 2): 256 / 288 tiles = ONE wave of the 296 CTA slots where
+// 128-wide tiles give 384 / 432 (1.3 - 1.5 waves), and a 192-wide MMA takes 96 cycles, so two co-resident issuers (~530 cycles per
+// k-block each, profiles/r2_gemm_decomposition.md) keep the tensor pipe ~90 % busy instead of ~78 %.  The 256-wide form:
 // 128x256 tiles at TWO CTAs per SM -- a 256-wide MMA takes 128 cycles, so the one-issuer limit (134 cycles per MMA) does not
 // bite, and two CTAs keep both the tensor pipe and the ~98 B/clk operand ingest busy; paid for with a 2-stage 48 KB ring, a
 // single-buffered 256-column accumulator and the bias read through L1 instead of shared memory (the budget is 96 bytes short).
 template <int BLOCK_N, bool LN, bool EPI8 = LN, int MODE = 0>
 struct PCfg {
     static constexpr bool WIDE2 = MODE == 2;
-    static_assert(!WIDE2 || (BLOCK_N == 256 && !LN), "WIDE2 is the 256-wide plain tile");
+    static_assert(!WIDE2 || ((BLOCK_N == 256 || BLOCK_N == 192) && !LN), "WIDE2 is the 192- / 256-wide plain tile");
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
@@ -76,7 +79,7 @@ struct PCfg {
     // LN-only pieces (gamma, beta, cluster partials) cost nothing in the plain kernel, whose budget is 233472 / 2 - 1024
     static constexpr int kLnAux = LN ? 2 * BLOCK_N * 4 + 4 * kBlockM * 8 : 0;
     // plain: ONE bias slice (the tile-end barrier of the epilogue warps protects it); LN keeps bias | gamma | beta resident
-    static constexpr bool kBiasInSmem = !WIDE2;
+    static constexpr bool kBiasInSmem = !WIDE2 || BLOCK_N == 192;     // the 192-wide ring leaves room for the bias slice
     static constexpr int kBiasFloats = LN ? 2 * BLOCK_N : (kBiasInSmem ? BLOCK_N : 0);
     static constexpr int kSmemAux = kBiasFloats * 4 + kLnAux + kNumBars * 8 + 16 + kXposeBytes;
     // no alignment slack: the dynamic shared-memory window starts 1024-aligned (checked at kernel entry).  An SM has 233472
@@ -617,7 +620,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     for (int i = et; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
                     epi_bar_sync<kEpiThreads>();
                 } else {
-                    bias_t = p.bias + n0;                  // WIDE2: straight from global / L1 (host guarantees bias != null, N % 256 == 0)
+                    bias_t = p.bias + n0;                  // WIDE2 / 256: straight from global / L1 (host guarantees bias != null, N % 256 == 0)
                 }
                 // LayerNorm fold: this row's statistics, computed while the main loop runs (the epilogue warps are idle until the
                 // accumulator is ready).  a_*: pending LayerNorm of the A operand (MODE 4); r_*: of the residual (MODE 5).
