@@ -412,7 +412,9 @@ struct vb200_engine {
                                // GEMM epilogues cost more than the row kernels they replace (measured: 36.9 k vs 40.8 k pairs/s
                                // at batch 64, profiles/r2_ln_fold.md) -- default stays GEMM (fp32 out) + row LayerNorm kernel
     std::set<std::string> fold_out_t, fold_out_v;   // stages ("T3", "C0", "E", ...) whose OUTPUT LayerNorm stays pending
-    bool wide192 = true;       // VB200_BN192=0: never pick the 128x192 tile (A/B)
+    bool wide192 = false;      // VB200_BN192=1: 128x192 tiles for GEMMs that need more than one wave of 128-wide ones.  Faster per
+                               // launch (FFN-in 18.5 -> 16.2 us, image QKV 16.9 -> 14.9 us, 973 TFLOP/s) but the STEP is 3 % slower
+                               // with them (38.8 k vs 40.1 k pairs/s, profiles/r2_tile192.md) -- opt-in
     bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two

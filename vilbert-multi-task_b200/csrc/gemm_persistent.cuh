@@ -20,6 +20,7 @@
 //   D[M,N] = epilogue( A[M,K] (16-bit, row-major)  x  W[N,K]^T (16-bit, nn.Linear layout = K-major) ), fp32 accumulate.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace vb {
@@ -957,7 +958,12 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
         if (resident <= 0) return cudaErrorInvalidConfiguration;
         grid = dim3(cluster, std::min(m_tiles, resident), 1);
     } else {
-        grid = dim3(std::min(m_tiles * n_tiles, num_sms() * Cfg::kMinBlocks), 1, 1);
+        // persistent grid: at most `slots` CTAs.  Default = every resident slot (kMinBlocks per SM).  VB200_GRID_PCT (experiment):
+        // percentage of that, e.g. 50 = one CTA per SM -- each CTA then walks several tiles (epilogue of tile i under the MMAs of
+        // tile i+1) and leaves the SM's second slot to whatever kernel of the other ViLBERT stream / batch is in flight.
+        static const int pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 100; return (v >= 10 && v <= 100) ? v : 100; }();
+        const int slots = std::max(1, num_sms() * Cfg::kMinBlocks * pct / 100);
+        grid = dim3(std::min(m_tiles * n_tiles, slots), 1, 1);
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
