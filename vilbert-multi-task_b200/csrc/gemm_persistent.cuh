@@ -958,10 +958,13 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
         if (resident <= 0) return cudaErrorInvalidConfiguration;
         grid = dim3(cluster, std::min(m_tiles, resident), 1);
     } else {
-        // persistent grid: at most `slots` CTAs.  Default = every resident slot (kMinBlocks per SM).  VB200_GRID_PCT (experiment):
-        // percentage of that, e.g. 50 = one CTA per SM -- each CTA then walks several tiles (epilogue of tile i under the MMAs of
-        // tile i+1) and leaves the SM's second slot to whatever kernel of the other ViLBERT stream / batch is in flight.
-        static const int pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 100; return (v >= 10 && v <= 100) ? v : 100; }();
+        // Persistent grid: two thirds of the resident CTA slots (197 of 296), not all of them.  A GEMM with more tiles than that
+        // (QKV, FFN-in at batch 64) then has CTAs that walk two tiles -- epilogue of tile i under the MMAs of tile i+1 -- and leaves
+        // slots to whichever kernel of the other ViLBERT stream / the other in-flight batch is runnable, which de-synchronises the two
+        // CTAs of an SM (two CTAs of ONE kernel run in lock-step: same prologue, same epilogue, tensor pipe idle in both).
+        // Measured, two batches in flight, 200-step runs: 100 % 40.5-40.9 k pairs/s | 85 % 40.9-41.0 | 75 % 41.5-41.8 | 67 % 41.7-41.9 |
+        // 60 % 41.3 | 50 % 41.6-41.8; timed alone a launch is ~8 % slower (profiles/r2_grid_size.md).  VB200_GRID_PCT overrides.
+        static const int pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 67; return (v >= 10 && v <= 100) ? v : 67; }();
         const int slots = std::max(1, num_sms() * Cfg::kMinBlocks * pct / 100);
         grid = dim3(std::min(m_tiles * n_tiles, slots), 1, 1);
     }
