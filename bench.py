@@ -331,6 +331,10 @@ def measure_vqa(args, model, reqs, dev, world, rank, local_rank, select, with_pr
             f["launches"] += 1; f["ms"] += o["ms"]; f["flops"] += o["flops"]
         res["fam"] = fam
         res["top"] = max((o for o in ops if o["kind"] == "gemm"), key=lambda o: o["flops"])
+        # the same GEMM launches with every resident CTA slot as their grid: what a launch does with the GPU to itself
+        # (production starts 2/3 of the slots, which is slower alone and faster in the step -- profiles/r2_grid_size.md)
+        full = [o for o in model.profile_ops(B, Tin, V, select, iters=5, grid_pct=100) if o["kind"] == "gemm"]
+        res["gemm_full_grid_tflops"] = sum(o["flops"] for o in full) / (sum(o["ms"] for o in full) * 1e-3) / 1e12
     return res
 
 
@@ -414,6 +418,9 @@ def run_vqa(args):
                          "avg_launch_us": 1e3 * g["ms"] / g["launches"],
                          "largest_gemm": {"M": top["dims"][0], "N": top["dims"][1], "K": top["dims"][2], "us": 1e3 * top["ms"],
                                           "tflops": top["flops"] / (top["ms"] * 1e-3) / 1e12},
+                         "achieved_full_grid": m["gemm_full_grid_tflops"], "frac_full_grid": m["gemm_full_grid_tflops"] / pk["bf16_burst"],
+                         "grid_note": "achieved/frac: the launches as the step issues them (persistent grid = 2/3 of the 296 CTA slots); "
+                                      "*_full_grid: the same launches with all slots, i.e. each kernel alone on the GPU",
                          "share_of_step": g["ms"] / serial_ms,
                          "families_ms": {k: round(v["ms"], 4) for k, v in fam.items()},
                          "whole_step_tflops": tflops, "whole_step_frac": tflops / step_peak,

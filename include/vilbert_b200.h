@@ -181,6 +181,10 @@ int vb200_forward_host_slot(vb200_handle h, const vb200_inputs* in, const vb200_
 int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select,
                     int64_t* n_launches, double* flops);
 int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
+/* Run-time knobs: "max_plans" (plan-cache bound); "profile_grid_pct" (0 or 10..100): the NEXT vb200_profile_ops call launches every
+ * GEMM with this percentage of the resident CTA slots as its persistent grid (production: two thirds, profiles/r2_grid_size.md) --
+ * for reporting what a launch does when it has the GPU to itself; forwards are never affected. */
+int vb200_set_option(vb200_handle h, const char* key, int64_t value);
 /* Per-launch device time of one forward of this shape (after at least one vb200_forward of it): every kernel of the plan is
  * captured 8x into its own CUDA graph and replayed `iters` times between two CUDA events (no host launch gaps).  kinds: 0 GEMM, 1 self-attention,
  * 2 co-attention, 3 narrow head, 4 LayerNorm; dims[4*i..] = {M, N, K, act|16*fusedLN} for GEMMs.  Profiling aid for bench.py. */

@@ -452,6 +452,7 @@ struct vb200_engine {
     float* lm_bias = nullptr;
     std::map<std::string, HostTensor> sd;
     std::map<std::vector<int64_t>, std::unique_ptr<Plan>> plans;
+    int profile_grid_pct = 0;       // vb200_set_option("profile_grid_pct"): persistent-grid override for vb200_profile_ops only
     uint64_t use_clock = 0;         // LRU clock of the plan cache
     size_t max_plans = 24;          // VB200_MAX_PLANS: least-recently-used plans beyond this are destroyed (workspace + graph)
     cudaStream_t side_stream = nullptr;
@@ -1255,6 +1256,7 @@ struct vb200_engine {
                 else {
                     GemmEpilogue e = op.ep;
                     e.tmap_c_host = e.tma_store ? &op.tc : nullptr;       // Op objects move when the list grows: bind here
+                    e.grid_pct = profile_grid_pct;                        // 0 outside vb200_profile_ops
                     const cudaError_t le = vb::launch_gemm_persistent(op.ta, op.tb, e, op.block_n, op.ln, st);
                     if (le != cudaSuccess)
                         fail(VB200_ERR_CUDA, "GEMM launch failed: %s (layer %s, M=%d N=%d K=%d act=%d block_n=%d cluster_ln=%d ln_mode=%d split16=%d tma_store=%d)",
@@ -1758,7 +1760,10 @@ int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n
         CUDA_CHECK(cudaSetDevice(h->opt.device));
         Plan* pl = h->get_plan(batch, n_tokens, n_regions, select & VB200_OUT_ALL);
         std::vector<double> t;
+        struct Reset { vb200_engine* e; int keep; ~Reset() { e->profile_grid_pct = keep; } } reset{h, h->profile_grid_pct};
         h->profile_ops(*pl, iters < 1 ? 1 : iters, t);
+        h->profile_grid_pct = 0;          // the override never leaks into forwards (plans are captured without it anyway)
+        reset.keep = 0;
         const int n = static_cast<int>(pl->ops.size());
         *n_ops = n;
         for (int i = 0; i < n && i < max_ops; ++i) {
@@ -1774,6 +1779,20 @@ int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n
                                                       : op.heads;
             }
         }
+    });
+}
+
+int vb200_set_option(vb200_handle h, const char* key, int64_t value) {
+    if (h == nullptr || key == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        const std::string k = key;
+        if (k == "profile_grid_pct") {
+            if (value != 0 && (value < 10 || value > 100)) fail(VB200_ERR_INVALID, "profile_grid_pct must be 0 or 10..100");
+            h->profile_grid_pct = static_cast<int>(value);
+        } else if (k == "max_plans") {
+            if (value < 1) fail(VB200_ERR_INVALID, "max_plans must be positive");
+            h->max_plans = static_cast<size_t>(value);
+        } else fail(VB200_ERR_INVALID, "unknown option \"%s\"", key);
     });
 }
 

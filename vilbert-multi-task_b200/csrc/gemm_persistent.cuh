@@ -964,7 +964,8 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
         // CTAs of an SM (two CTAs of ONE kernel run in lock-step: same prologue, same epilogue, tensor pipe idle in both).
         // Measured, two batches in flight, 200-step runs: 100 % 40.5-40.9 k pairs/s | 85 % 40.9-41.0 | 75 % 41.5-41.8 | 67 % 41.7-41.9 |
         // 60 % 41.3 | 50 % 41.6-41.8; timed alone a launch is ~8 % slower (profiles/r2_grid_size.md).  VB200_GRID_PCT overrides.
-        static const int pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 67; return (v >= 10 && v <= 100) ? v : 67; }();
+        static const int env_pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 67; return (v >= 10 && v <= 100) ? v : 67; }();
+        const int pct = (ep.grid_pct >= 10 && ep.grid_pct <= 100) ? ep.grid_pct : env_pct;      // per-launch override (profiling: timed alone)
         const int slots = std::max(1, num_sms() * Cfg::kMinBlocks * pct / 100);
         grid = dim3(std::min(m_tiles * n_tiles, slots), 1, 1);
     }

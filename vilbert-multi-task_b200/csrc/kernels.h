@@ -45,6 +45,7 @@ struct GemmEpilogue {
     const float* res_beta;
     float2* out_stats;            // MODE 5: this GEMM's own row statistics, [N / 32][stats_ld]
     int stats_ld;                 // row capacity of every stats array of this launch (>= M)
+    int grid_pct;                 // 0: default persistent grid (2/3 of the CTA slots, launch_p); 10..100: this percentage of them
     int ln_mode;                  // 0 none, 4 fold-in (consumer), 5 pre-LayerNorm output + statistics (producer)
     int debug;                    // timing decomposition only (VB200_DEBUG through vb200_linear): 1 = issue no MMA, 2 = no epilogue
                                   // stores, 4 = no operand loads (the ring is "filled" by plain arrives); results are garbage

@@ -196,8 +196,11 @@ class VILBertForVLTasks(object):
                 self._handle)
         return n.value, f.value
 
-    def profile_ops(self, batch, n_tokens, n_regions, select=L.OUT_TASK_HEADS, iters=5):
-        """Per-launch device times (ms) of one forward, CUDA events around every kernel (eager, one stream)."""
+    def profile_ops(self, batch, n_tokens, n_regions, select=L.OUT_TASK_HEADS, iters=5, grid_pct=0):
+        """Per-launch device times (ms) of one forward: every kernel replayed alone from its own CUDA graph between two events.
+        grid_pct (10..100): persistent-grid size of the GEMMs for THIS measurement only (production: 2/3 of the CTA slots)."""
+        if grid_pct:
+            L.check(L.load().vb200_set_option(self._handle, b"profile_grid_pct", int(grid_pct)), self._handle)
         cap = 2048
         n = C.c_int32()
         kinds = (C.c_int32 * cap)()
