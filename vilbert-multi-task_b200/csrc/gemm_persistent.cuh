@@ -967,7 +967,12 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
         static const int env_pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 67; return (v >= 10 && v <= 100) ? v : 67; }();
         const int pct = (ep.grid_pct >= 10 && ep.grid_pct <= 100) ? ep.grid_pct : env_pct;      // per-launch override (profiling: timed alone)
         const int slots = std::max(1, num_sms() * Cfg::kMinBlocks * pct / 100);
-        grid = dim3(std::min(m_tiles * n_tiles, slots), 1, 1);
+        // balanced walk: every CTA gets the same number of tiles (+-1): tiles = 288, cap 197 -> 144 CTAs x 2 instead of 91 x 2 + 106 x 1
+        static const bool balance = [] { const char* e = getenv("VB200_GRID_BALANCE"); return e == nullptr || atoi(e) != 0; }();
+        const int tiles = m_tiles * n_tiles;
+        int g = std::min(tiles, slots);
+        if (balance && tiles > slots) { const int per = (tiles + slots - 1) / slots; g = (tiles + per - 1) / per; }
+        grid = dim3(g, 1, 1);
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
