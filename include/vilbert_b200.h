@@ -259,6 +259,12 @@ int vb200_linear_split(const void* x16, int64_t ld_x, const void* w16, int64_t l
 int vb200_layernorm(const float* y, int64_t ld_y, const float* residual, int64_t ld_res, const float* gamma, const float* beta,
                     float eps, float* out_f32, int64_t ld_f32, void* out_16, int64_t ld_16, int64_t M, int64_t N,
                     int32_t act_fp16, void* cuda_stream);
+/* Two dependent GEMMs in one launch (vilbert-multi-task_b200/csrc/gemm_chain.cu): h = act(x w1^T + b1) (16-bit, [M, N1]) and
+ * y = h w2^T + b2 ([M, N2], 16-bit and/or fp32).  sync_ints: device memory, M / 128 (rounded up) + 2 ints, zero before the first
+ * call (the kernel leaves it zeroed).  Results are bit-identical to two vb200_linear calls. */
+int vb200_linear_chain(const void* x16, int64_t ld_x, const void* w1, int64_t ld_w1, const float* b1, int32_t act, void* h16, int64_t ld_h,
+                       const void* w2, int64_t ld_w2, const float* b2, void* y16, int64_t ld_y16, float* y_f32, int64_t ld_y_f32, int64_t M,
+                       int64_t N1, int64_t K1, int64_t N2, int32_t act_fp16, void* sync_ints, void* cuda_stream);
 /* The GEMM with the LayerNorm fold epilogues (vilbert-multi-task_b200/csrc/gemm_persistent.cuh, row_stats).  Statistics arrays are
  * float2 (mean, M2 = sum (x - mean)^2) per row and 32-column chunk, laid out [N_src / 32][stats_ld].
  * mode 5 (producer): u = x w^T + bias + residual, where the residual is res, or LayerNorm_{res_gamma,res_beta}(res) rebuilt from

@@ -465,3 +465,36 @@ def test_layernorm_fold_chain(M, H, N2, act, act_dt, parity_log):
     assert (v16.double() - v_ref).abs().max().item() < (1e-2 if f16 else 8e-2)
     # (c) the row-LayerNorm kernel with the same pending residual is exercised through the model tests (boundary layers)
     parity_log(test="ln_fold_producer", M=M, H=H, dtype=str(act_dt), max_abs_err=err_b)
+
+
+@pytest.mark.parametrize("act_dt", ACT)
+@pytest.mark.parametrize("M,K1,N1,N2,act", [(1984, 768, 3072, 768, 1), (2304, 1024, 1024, 1024, 1), (300, 256, 384, 128, 0),
+                                             (15872, 768, 3072, 768, 1), (1000, 128, 256, 1024, 2)])
+def test_gemm_chain(M, K1, N1, N2, act, act_dt, parity_log):
+    """Two dependent GEMMs in one persistent launch (FFN-in -> FFN-out, dynamic tile list with cross-CTA dependencies):
+    bit-identical to two separate launches, repeatable (the kernel re-zeroes its counters), and correct vs fp64 math."""
+    L, lib = _lib()
+    f16 = 1 if act_dt == torch.float16 else 0
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(M, K1, generator=g, device="cuda").to(act_dt)
+    w1 = (torch.randn(N1, K1, generator=g, device="cuda") / math.sqrt(K1)).to(act_dt)
+    b1 = 0.1 * torch.randn(N1, generator=g, device="cuda")
+    w2 = (torch.randn(N2, N1, generator=g, device="cuda") / math.sqrt(N1)).to(act_dt)
+    b2 = 0.1 * torch.randn(N2, generator=g, device="cuda")
+    h_ref, _ = run_linear(x, w1, b1, act=act, want_f32=False)
+    _, y_ref = run_linear(h_ref, w2, b2, want_bf16=False)
+    sync = torch.zeros((M + 127) // 128 + 2, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for rep in range(3):
+        h = torch.zeros(M, N1, dtype=act_dt, device="cuda")
+        y = torch.full((M, N2), float("nan"), device="cuda")
+        L.check(lib.vb200_linear_chain(_ptr(x), K1, _ptr(w1), K1, _ptr(b1), act, _ptr(h), N1, _ptr(w2), N1, _ptr(b2), None, 0, _ptr(y), N2,
+                                       M, N1, K1, N2, f16, _ptr(sync), st), None)
+        torch.cuda.synchronize()
+        assert torch.equal(h, h_ref), rep
+        assert torch.equal(y, y_ref), (rep, float((y - y_ref).abs().max()))
+        assert int(sync.abs().sum()) == 0
+    ref = ref_linear(ref_linear(x, w1, b1, act=act).to(act_dt), w2, b2)
+    err = (y - ref).abs().max().item()
+    parity_log(test="gemm_chain", M=M, K1=K1, N1=N1, N2=N2, act=act, dtype=str(act_dt), max_abs_err=err)
+    assert err < (5e-3 if f16 else 4e-2), err

@@ -336,7 +336,13 @@ struct Op {
     int block_n = 128;
     bool ln = false;
     bool pair = false;             // CTA-pair kernel (cta_group::2); tb then has box rows block_n / 2
+    // chained GEMM (gemm_chain.cu): this GEMM's 16-bit output is the A operand of a second one issued from the same launch
+    CUtensorMap ta2, tb2;
+    GemmEpilogue ep2;
+    int* chain_sync = nullptr;
+    double flops2 = 0;
     // fp32 attention (attention_f32.cu): fp32-parity mode and the attention-probability output
+    const void* a_ptr = nullptr;   // GEMM: the A operand (chain detection)
     const void *f_q = nullptr, *f_k = nullptr, *f_v = nullptr;
     int f_ld_q = 0, f_ld_kv = 0, f_in = 0, f_Lq = 0, f_Lk = 0, f_ctx_mode = 0, f_ld_ctx = 0;
     const float* f_mask = nullptr;
@@ -412,6 +418,7 @@ struct vb200_engine {
                                // GEMM epilogues cost more than the row kernels they replace (measured: 36.9 k vs 40.8 k pairs/s
                                // at batch 64, profiles/r2_ln_fold.md) -- default stays GEMM (fp32 out) + row LayerNorm kernel
     std::set<std::string> fold_out_t, fold_out_v;   // stages ("T3", "C0", "E", ...) whose OUTPUT LayerNorm stays pending
+    bool chain_ffn = true;     // VB200_CHAIN=0: FFN-in and FFN-out as two launches (round 1) instead of one chained launch
     bool wide192 = false;      // VB200_BN192=1: 128x192 tiles for GEMMs that need more than one wave of 128-wide ones.  Faster per
                                // launch (FFN-in 18.5 -> 16.2 us, image QKV 16.9 -> 14.9 us, 973 TFLOP/s) but the STEP is 3 % slower
                                // with them (38.8 k vs 40.1 k pairs/s, profiles/r2_tile192.md) -- opt-in
@@ -886,6 +893,7 @@ struct vb200_engine {
         }
         if (tma_store_enabled && !op.pair && !op.ln) setup_tma_store(&op.tc, e);
         op.flops = 2.0 * a_rows * W.N * W.K;
+        op.a_ptr = A;
         pl.flops += op.flops;
         pl.ops.push_back(op);
         if (split_ln) {
@@ -1149,6 +1157,7 @@ struct vb200_engine {
         for (size_t i = n_before_heads; i < ops.size(); ++i) ops[i].tag = "heads";
         for (Op& op : ops) if (op.kind == Op::ROWDOT) pl.flops += op.flops;
 
+        link_chains(pl);
         link_pdl(pl);
         // One eager pass first: opts kernels into their shared-memory sizes and surfaces launch-configuration
         // errors with a real message (errors inside a capture only invalidate the capture).
@@ -1252,7 +1261,12 @@ struct vb200_engine {
     void launch_op(const Op& op, cudaStream_t st) {
         switch (op.kind) {
             case Op::GEMM:
-                if (op.pair) CUDA_CHECK(vb::launch_gemm_pair(op.ta, op.tb, op.ep, op.block_n, st));
+                if (op.chain_sync != nullptr) {
+                    const cudaError_t le = vb::launch_gemm_chain(op.ta, op.tb, op.ep, op.ta2, op.tb2, op.ep2, op.chain_sync, st);
+                    if (le != cudaSuccess)
+                        fail(VB200_ERR_CUDA, "chained GEMM launch failed: %s (layer %s, M=%d N1=%d K1=%d N2=%d)", cudaGetErrorString(le),
+                             op.tag ? op.tag : "?", op.ep.M, op.ep.N, op.ep.K, op.ep2.N);
+                } else if (op.pair) CUDA_CHECK(vb::launch_gemm_pair(op.ta, op.tb, op.ep, op.block_n, st));
                 else {
                     GemmEpilogue e = op.ep;
                     e.tmap_c_host = e.tma_store ? &op.tc : nullptr;       // Op objects move when the list grows: bind here
@@ -1363,6 +1377,39 @@ struct vb200_engine {
         }
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     }
+    // FFN-in -> FFN-out (and every other producer / consumer pair of plain 128-wide GEMMs that sit next to each other on one graph
+    // branch, the first writing only the 16-bit operand the second reads) become ONE chained launch (gemm_chain.cu).
+    void link_chains(Plan& pl) {
+        if (!chain_ffn || x3) return;
+        std::vector<Op> out;
+        out.reserve(pl.ops.size());
+        for (size_t i = 0; i < pl.ops.size(); ++i) {
+            Op a = pl.ops[i];
+            if (i + 1 < pl.ops.size() && a.kind == Op::GEMM && !a.chain_sync) {
+                const Op& b = pl.ops[i + 1];
+                auto plain = [](const Op& o) {
+                    const GemmEpilogue& e = o.ep;
+                    return o.kind == Op::GEMM && !o.pair && !o.ln && o.block_n == 128 && e.ln_mode == 0 && !e.split16 && e.res == nullptr &&
+                           e.mul == nullptr && e.gamma == nullptr && (e.N & 31) == 0 && e.act != vb::kActGeluExact;
+                };
+                if (plain(a) && plain(b) && a.stream == b.stream && b.sync == Op::NONE && a.ep.M == b.ep.M && a.ep.M >= 256 &&
+                    a.ep.out_bf16 != nullptr && a.ep.out_f32 == nullptr && (a.ep.ld_bf16 & 7) == 0 && b.a_ptr == a.ep.out_bf16 &&
+                    b.ep.K == a.ep.N && (b.ep.out_bf16 == nullptr || (b.ep.ld_bf16 & 7) == 0) && (b.ep.out_f32 == nullptr || (b.ep.ld_f32 & 3) == 0)) {
+                    a.ta2 = b.ta; a.tb2 = b.tb; a.ep2 = b.ep; a.flops2 = b.flops;
+                    const int m_tiles = (a.ep.M + 127) / 128;
+                    a.chain_sync = pl.mem.alloc_n<int>(m_tiles + 2);
+                    CUDA_CHECK(cudaMemset(a.chain_sync, 0, sizeof(int) * (m_tiles + 2)));
+                    a.ep.tma_store = 0; a.ep2.tma_store = 0;
+                    out.push_back(a);
+                    ++i;                       // b is issued by the same launch
+                    continue;
+                }
+            }
+            out.push_back(a);
+        }
+        pl.ops.swap(out);
+    }
+
     // PDL "medium" (default): additionally launch a GEMM programmatically when the kernel before it on its graph branch is a light one
     // (LayerNorm / attention trigger their dependents right after loading their inputs, so the GEMM's prologue -- barrier init,
     // TMEM allocation, descriptor prefetch -- overlaps the light kernel's math instead of following it).
@@ -1566,6 +1613,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
         if (const char* v = getenv("VB200_BN192")) eng->wide192 = (strcmp(v, "0") != 0);
+        if (const char* v = getenv("VB200_CHAIN")) eng->chain_ffn = (strcmp(v, "0") != 0);
         eng->ln_fold = o.ln_fold > 0;
         if (const char* v = getenv("VB200_LNFOLD")) eng->ln_fold = (strcmp(v, "0") != 0);
         if (eng->x3 || eng->fused_ln) eng->ln_fold = false;      // those modes keep every LayerNorm as its own step
@@ -1770,12 +1818,13 @@ int vb200_profile_ops(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n
             const Op& op = pl->ops[i];
             if (kinds) kinds[i] = static_cast<int>(op.kind);
             if (ms) ms[i] = t[i];
-            if (flops) flops[i] = op.flops;
+            if (flops) flops[i] = op.flops + op.flops2;
             if (dims) {
                 dims[4 * i + 0] = op.kind == Op::GEMM ? op.ep.M : (op.kind == Op::LAYERNORM ? op.ln_M : op.B);
                 dims[4 * i + 1] = op.kind == Op::GEMM ? op.ep.N : (op.kind == Op::LAYERNORM ? op.ln_N : op.La);
                 dims[4 * i + 2] = op.kind == Op::GEMM ? op.ep.K : op.Lb;
-                dims[4 * i + 3] = op.kind == Op::GEMM ? (op.ep.act | (op.ln ? 16 : 0) | (op.ep.ln_mode == 4 ? 32 : 0) | (op.ep.ln_mode == 5 ? 64 : 0))
+                dims[4 * i + 3] = op.kind == Op::GEMM ? (op.ep.act | (op.ln ? 16 : 0) | (op.ep.ln_mode == 4 ? 32 : 0) | (op.ep.ln_mode == 5 ? 64 : 0) |
+                                                         (op.chain_sync ? 128 : 0))
                                                       : op.heads;
             }
         }
@@ -1899,6 +1948,21 @@ int vb200_linear_ln(const void* x16, int64_t ld_x, const void* w16, int64_t ld_w
         e.res = res; e.ld_res = (int)ld_res; e.res_stats = static_cast<const float2*>(res_stats); e.res_parts = res_parts;
         e.res_gamma = res_gamma; e.res_beta = res_beta; e.out_stats = static_cast<float2*>(out_stats);
         CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, 128, false, static_cast<cudaStream_t>(cuda_stream)));
+    });
+}
+
+int vb200_linear_chain(const void* x16, int64_t ld_x, const void* w1, int64_t ld_w1, const float* b1, int32_t act, void* h16, int64_t ld_h,
+                       const void* w2, int64_t ld_w2, const float* b2, void* y16, int64_t ld_y16, float* y_f32, int64_t ld_y_f32, int64_t M,
+                       int64_t N1, int64_t K1, int64_t N2, int32_t act_fp16, void* sync_ints, void* cuda_stream) {
+    return op_guard([&] {
+        CUtensorMap ta0 = make_tmap(x16, M, K1, ld_x, 128, act_fp16 != 0), tb0 = make_tmap(w1, N1, K1, ld_w1, 128, act_fp16 != 0);
+        CUtensorMap ta1 = make_tmap(h16, M, N1, ld_h, 128, act_fp16 != 0), tb1 = make_tmap(w2, N2, N1, ld_w2, 128, act_fp16 != 0);
+        GemmEpilogue e0{}, e1{};
+        e0.M = e1.M = (int)M; e0.N = (int)N1; e0.K = (int)K1; e1.N = (int)N2; e1.K = (int)N1;
+        e0.bias = b1; e1.bias = b2; e0.act = act; e0.a_f16 = e0.out_f16 = e1.a_f16 = e1.out_f16 = act_fp16 ? 1 : 0;
+        e0.out_bf16 = static_cast<bf16*>(h16); e0.ld_bf16 = (int)ld_h;
+        e1.out_bf16 = static_cast<bf16*>(y16); e1.ld_bf16 = (int)ld_y16; e1.out_f32 = y_f32; e1.ld_f32 = (int)ld_y_f32;
+        CUDA_CHECK(vb::launch_gemm_chain(ta0, tb0, e0, ta1, tb1, e1, static_cast<int*>(sync_ints), static_cast<cudaStream_t>(cuda_stream)));
     });
 }
 

@@ -60,6 +60,9 @@ int num_sms_host();          // SM count of the current device (148 on B200)
 // CTA-pair kernel (gemm_pair.cu, tcgen05 cta_group::2, 256 x block_n tile per pair); tmap_b box rows = block_n / 2
 cudaError_t launch_gemm_pair(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep, int block_n,
                              cudaStream_t stream);
+// Two dependent GEMMs (FFN-in -> FFN-out) in one persistent launch with a dynamic tile list (gemm_chain.cu); sync: (M tiles + 2) zeroed ints
+cudaError_t launch_gemm_chain(const CUtensorMap& ta0, const CUtensorMap& tb0, const GemmEpilogue& ep0, const CUtensorMap& ta1,
+                              const CUtensorMap& tb1, const GemmEpilogue& ep1, int* sync, cudaStream_t st);
 cudaError_t launch_gemm_persistent_plain(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmEpilogue& ep,
                                          int block_n, cudaStream_t st);
 
