@@ -183,7 +183,9 @@ int vb200_plan_info(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_r
 int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
 /* Run-time knobs: "max_plans" (plan-cache bound); "profile_grid_pct" (0 or 10..100): the NEXT vb200_profile_ops call launches every
  * GEMM with this percentage of the resident CTA slots as its persistent grid (production: two thirds, profiles/r2_grid_size.md) --
- * for reporting what a launch does when it has the GPU to itself; forwards are never affected. */
+ * for reporting what a launch does when it has the GPU to itself; forwards are never affected.  "chain_ffn" (0/1): issue every
+ * FFN-in -> FFN-out pair as ONE chained persistent launch (csrc/gemm_chain.cu: dynamic tile list + per-row-panel dependency counters;
+ * same bits, measured slower at batch 64, profiles/r2_chain.md -> off by default); changing it drains the device and drops cached plans. */
 int vb200_set_option(vb200_handle h, const char* key, int64_t value);
 /* Per-launch device time of one forward of this shape (after at least one vb200_forward of it): every kernel of the plan is
  * captured 8x into its own CUDA graph and replayed `iters` times between two CUDA events (no host launch gaps).  kinds: 0 GEMM, 1 self-attention,

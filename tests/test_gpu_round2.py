@@ -389,3 +389,28 @@ def test_layernorm_fold_vs_unfolded_and_oracle(tiny_oracle, full_oracle, parity_
         assert torch.equal(one[0], a[0][1:2])
         fold.close()
         plain.close()
+
+
+# ----------------------------------------------------------------------------------------------- chained FFN launch
+def test_chained_ffn_launch_is_bit_identical(full_oracle, parity_log):
+    """set_option("chain_ffn", 1): every FFN-in -> FFN-out pair becomes one persistent launch with a dynamic tile list and per-row-panel
+    dependency counters (csrc/gemm_chain.cu).  Same tiles, same accumulation order: every output keeps its bits; 30 launches fewer."""
+    from oracle import vilbert_ref as R
+    from vilbert_b200 import _lib as L
+    inp = list(R.make_inputs(16, 30, 36, seed=93, pad_regions=2))      # 16 x 31 rows >= 256: the engine chains from M = 256 up
+    dev = [t.cuda() for t in inp]
+    eng = _engine(full_oracle)
+    plain = [t.clone() for t in eng(*dev)[:9]]
+    n_plain, _ = eng.plan_info(16, 30, 36, L.OUT_TASK_HEADS)
+    eng.set_option("chain_ffn", 1)
+    n_chain, _ = eng.plan_info(16, 30, 36, L.OUT_TASK_HEADS)
+    for rep in range(3):                                                # the dependency counters reset themselves between launches
+        chained = eng(*dev)[:9]
+        torch.cuda.synchronize()
+        for a, b in zip(plain, chained):
+            assert torch.equal(a, b)
+    parity_log(test="chain_ffn_launches", launches_chained=n_chain, launches_plain=n_plain)
+    assert n_plain - n_chain == 30
+    eng.set_option("chain_ffn", 0)
+    assert eng.plan_info(16, 30, 36, L.OUT_TASK_HEADS)[0] == n_plain
+    eng.close()

@@ -418,7 +418,8 @@ struct vb200_engine {
                                // GEMM epilogues cost more than the row kernels they replace (measured: 36.9 k vs 40.8 k pairs/s
                                // at batch 64, profiles/r2_ln_fold.md) -- default stays GEMM (fp32 out) + row LayerNorm kernel
     std::set<std::string> fold_out_t, fold_out_v;   // stages ("T3", "C0", "E", ...) whose OUTPUT LayerNorm stays pending
-    bool chain_ffn = true;     // VB200_CHAIN=0: FFN-in and FFN-out as two launches (round 1) instead of one chained launch
+    bool chain_ffn = false;    // VB200_CHAIN=1 / vb200_set_option("chain_ffn", 1): FFN-in and FFN-out as ONE chained launch (gemm_chain.cu);
+                               // bit-identical, measured slower at batch 64 (profiles/r2_chain.md) -> opt-in
     bool wide192 = false;      // VB200_BN192=1: 128x192 tiles for GEMMs that need more than one wave of 128-wide ones.  Faster per
                                // launch (FFN-in 18.5 -> 16.2 us, image QKV 16.9 -> 14.9 us, 973 TFLOP/s) but the STEP is 3 % slower
                                // with them (38.8 k vs 40.1 k pairs/s, profiles/r2_tile192.md) -- opt-in
@@ -1841,6 +1842,13 @@ int vb200_set_option(vb200_handle h, const char* key, int64_t value) {
         } else if (k == "max_plans") {
             if (value < 1) fail(VB200_ERR_INVALID, "max_plans must be positive");
             h->max_plans = static_cast<size_t>(value);
+        } else if (k == "chain_ffn") {
+            // changes how plans are built: drop the cached ones (the device is drained first, a plan may still be executing)
+            if ((value != 0) != h->chain_ffn) {
+                CUDA_CHECK(cudaDeviceSynchronize());
+                h->plans.clear();
+                h->chain_ffn = value != 0;
+            }
         } else fail(VB200_ERR_INVALID, "unknown option \"%s\"", key);
     });
 }

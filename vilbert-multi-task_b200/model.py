@@ -196,6 +196,10 @@ class VILBertForVLTasks(object):
                 self._handle)
         return n.value, f.value
 
+    def set_option(self, key, value):
+        """Run-time knobs of the engine (include/vilbert_b200.h, vb200_set_option): "max_plans", "chain_ffn", "profile_grid_pct"."""
+        L.check(L.load().vb200_set_option(self._handle, key.encode(), int(value)), self._handle)
+
     def profile_ops(self, batch, n_tokens, n_regions, select=L.OUT_TASK_HEADS, iters=5, grid_pct=0):
         """Per-launch device times (ms) of one forward: every kernel replayed alone from its own CUDA graph between two events.
         grid_pct (10..100): persistent-grid size of the GEMMs for THIS measurement only (production: 2/3 of the CTA slots)."""
@@ -209,7 +213,7 @@ class VILBertForVLTasks(object):
         dims = (C.c_int32 * (4 * cap))()
         L.check(L.load().vb200_profile_ops(self._handle, batch, n_tokens, n_regions, select, iters, cap, C.byref(n), kinds, ms,
                                            fl, dims), self._handle)
-        names = {0: "gemm", 1: "self_attention", 2: "co_attention", 3: "rowdot", 4: "layernorm"}
+        names = {0: "gemm", 1: "self_attention", 2: "co_attention", 3: "rowdot", 4: "layernorm", 5: "attention_f32"}
         return [dict(kind=names.get(kinds[i], "?"), ms=ms[i], flops=fl[i], dims=list(dims[4 * i:4 * i + 4]))
                 for i in range(min(n.value, cap))]
 
