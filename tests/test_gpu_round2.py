@@ -400,13 +400,14 @@ def test_chained_ffn_launch_is_bit_identical(full_oracle, parity_log):
     inp = list(R.make_inputs(16, 30, 36, seed=93, pad_regions=2))      # 16 x 31 rows >= 256: the engine chains from M = 256 up
     dev = [t.cuda() for t in inp]
     eng = _engine(full_oracle)
-    plain = [t.clone() for t in eng(*dev)[:9]]
+    plain = [t.clone() for t in eng(*dev)[:9] if t is not None]
     n_plain, _ = eng.plan_info(16, 30, 36, L.OUT_TASK_HEADS)
     eng.set_option("chain_ffn", 1)
     n_chain, _ = eng.plan_info(16, 30, 36, L.OUT_TASK_HEADS)
     for rep in range(3):                                                # the dependency counters reset themselves between launches
-        chained = eng(*dev)[:9]
+        chained = [t for t in eng(*dev)[:9] if t is not None]
         torch.cuda.synchronize()
+        assert len(chained) == len(plain) >= 7
         for a, b in zip(plain, chained):
             assert torch.equal(a, b)
     parity_log(test="chain_ffn_launches", launches_chained=n_chain, launches_plain=n_plain)

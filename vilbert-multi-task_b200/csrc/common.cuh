@@ -248,27 +248,25 @@ __device__ __forceinline__ float erf_fast(float x) {
 }
 // GELU, erf form: x * 0.5 * (1 + erf(x / sqrt(2)))   ([UPSTREAM] vilbert.py `gelu`)
 __device__ __forceinline__ float gelu_erf_as(float x) { return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
-// Same function, 16 issue slots and no MUFU: erf(z) = z * P(min(z^2, 9)) clamped to [-1, 1] (minimax fit of degree 8 in z^2 on
-// |z| <= 3, |error| < 2.6e-5 in fp32 Horner form; beyond |z| = 3 the product z * P(9) = z / 3.00007 leaves [-1, 1] and the clamp
-// returns erf = +-1 EXACTLY, so a strongly negative pre-activation gives -0 and a strongly positive one x itself -- the earlier
-// form clamped z instead and returned -1.1e-5 * x there).  |gelu error| <= 6.7e-5 (at x = 4.24, value 4.24), i.e. < 7 % of half
-// an fp16 ulp there; the A&S form above is 30x more accurate but costs ~27 slots incl. 2 MUFU, and the FFN-in epilogue is
-// instruction-issue bound (16 K evaluations per 128x128 tile).  Coefficients: scripts/fit_gelu.py.
+// Same function, 11 issue slots and no MUFU: gelu(x) = x * Phi(x) with Phi(x) ~ sat(0.5 + x * Q(x^2)), Q of degree 8 in x^2 fitted on
+// |x| <= 4.25 with weight |x| (scripts/fit_gelu.py), sat = the FFMA's free saturation to [0, 1].  Q's leading coefficient is positive, so
+// beyond the fitted range x * Q(x^2) runs monotonically to +-inf and the saturation returns Phi = 1 / 0 EXACTLY: a strongly negative
+// pre-activation gives -0 and a strongly positive one x itself, with no range clamp (round 1 clamped z and returned -1.1e-5 * x there;
+// the first round-2 form needed min(z^2, 9) and a two-sided clamp: 16 slots).  |gelu error| <= 4.3e-5 over the whole fp32 range, < 5 % of
+// half an fp16 ulp at the magnitude where it occurs; the A&S form above is 30x more accurate but costs ~27 slots incl. 2 MUFU, and the
+// FFN-in epilogue is FP32-pipe bound (16 K evaluations per 128x128 tile; FFMA2 halves the issue slots, not the pipe time -- measured).
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = x * 0.70710678118654752440f;
-    const float u = fminf(z * z, 9.0f);
-    float p = 4.074150084e-08f;
-    p = fmaf(p, u, -1.944801170e-06f);
-    p = fmaf(p, u, 4.106021152e-05f);
-    p = fmaf(p, u, -5.110344500e-04f);
-    p = fmaf(p, u, 4.235417116e-03f);
-    p = fmaf(p, u, -2.510283515e-02f);
-    p = fmaf(p, u, 1.110793054e-01f);
-    p = fmaf(p, u, -3.753148615e-01f);
-    p = fmaf(p, u, 1.128268480e+00f);
-    const float e = fminf(fmaxf(z * p, -1.0f), 1.0f);
-    const float hx = 0.5f * x;
-    return fmaf(hx, e, hx);
+    const float u = x * x;
+    float q = 4.547042257e-11f;
+    q = fmaf(q, u, -4.515281038e-09f);
+    q = fmaf(q, u, 1.986152114e-07f);
+    q = fmaf(q, u, -5.147503089e-06f);
+    q = fmaf(q, u, 8.848903963e-05f);
+    q = fmaf(q, u, -1.079077483e-03f);
+    q = fmaf(q, u, 9.718777612e-03f);
+    q = fmaf(q, u, -6.619028002e-02f);
+    q = fmaf(q, u, 3.988192081e-01f);
+    return x * __saturatef(fmaf(x, q, 0.5f));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

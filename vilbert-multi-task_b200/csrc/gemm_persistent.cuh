@@ -965,11 +965,15 @@ cudaError_t launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
         // Measured, two batches in flight, 200-step runs: 100 % 40.5-40.9 k pairs/s | 85 % 40.9-41.0 | 75 % 41.5-41.8 | 67 % 41.7-41.9 |
         // 60 % 41.3 | 50 % 41.6-41.8; timed alone a launch is ~8 % slower (profiles/r2_grid_size.md).  VB200_GRID_PCT overrides.
         static const int env_pct = [] { const char* e = getenv("VB200_GRID_PCT"); const int v = e ? atoi(e) : 67; return (v >= 10 && v <= 100) ? v : 67; }();
-        const int pct = (ep.grid_pct >= 10 && ep.grid_pct <= 100) ? ep.grid_pct : env_pct;      // per-launch override (profiling: timed alone)
+        static const bool env_set = getenv("VB200_GRID_PCT") != nullptr;
+        const int tiles = m_tiles * n_tiles;
+        // From two full waves up (batch >= ~256) every CTA owns several tiles anyway and the full grid wins: batch 512, 45.3 k pairs/s
+        // at 67 %, 45.9 k at 100 % (profiles/r2_b512.md).
+        const int auto_pct = (!env_set && tiles >= 2 * num_sms() * Cfg::kMinBlocks) ? 100 : env_pct;
+        const int pct = (ep.grid_pct >= 10 && ep.grid_pct <= 100) ? ep.grid_pct : auto_pct;     // per-launch override (profiling: timed alone)
         const int slots = std::max(1, num_sms() * Cfg::kMinBlocks * pct / 100);
         // balanced walk: every CTA gets the same number of tiles (+-1): tiles = 288, cap 197 -> 144 CTAs x 2 instead of 91 x 2 + 106 x 1
         static const bool balance = [] { const char* e = getenv("VB200_GRID_BALANCE"); return e == nullptr || atoi(e) != 0; }();
-        const int tiles = m_tiles * n_tiles;
         int g = std::min(tiles, slots);
         if (balance && tiles > slots) { const int per = (tiles + slots - 1) / slots; g = (tiles + per - 1) / per; }
         grid = dim3(g, 1, 1);
