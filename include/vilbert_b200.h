@@ -187,6 +187,13 @@ int vb200_model_dim(vb200_handle h, const char* key, int64_t* value);
  * FFN-in -> FFN-out pair as ONE chained persistent launch (csrc/gemm_chain.cu: dynamic tile list + per-row-panel dependency counters;
  * same bits, measured slower at batch 64, profiles/r2_chain.md -> off by default); changing it drains the device and drops cached plans. */
 int vb200_set_option(vb200_handle h, const char* key, int64_t value);
+/* Profiling: after vb200_set_option(h, "timeline", 1) every tcgen05 GEMM launch of a forward records 16 stamps per CTA (0: clock64 at
+ * entry, 1: setup done, 2: first k-block landed [-DVB200_STAMPS builds], 8 / 9: %globaltimer ns at entry / exit, 10: last MMA committed,
+ * 11: tiles walked, 12: SM id).  Copies the stamps of the LAST forward run on (shape, select, slot): stamps[n_ops][304][16],
+ * dims[n_ops][4] = M, N, K, graph branch.  Synchronises the device.  scripts/step_timeline.py turns two slots' worth into per-SM
+ * occupancy figures. */
+int vb200_timeline(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select, int32_t slot, int32_t max_ops,
+                   int32_t* n_ops, int32_t* dims, int64_t* stamps);
 /* Per-launch device time of one forward of this shape (after at least one vb200_forward of it): every kernel of the plan is
  * captured 8x into its own CUDA graph and replayed `iters` times between two CUDA events (no host launch gaps).  kinds: 0 GEMM, 1 self-attention,
  * 2 co-attention, 3 narrow head, 4 LayerNorm; dims[4*i..] = {M, N, K, act|16*fusedLN} for GEMMs.  Profiling aid for bench.py. */

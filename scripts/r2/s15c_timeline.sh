@@ -1,0 +1,13 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out/r2
+O=gpurun_out/r2
+VB200_TMASTORE=0 timeout 300 python scripts/step_timeline.py --inflight 2 --out $O/s15c_timeline_if2_notma.json > $O/s15c_if2.log 2>&1 || tail -5 $O/s15c_if2.log
+python - <<PY
+import json
+for f in ("s15c_timeline_if2_notma",):
+    j = json.load(open("gpurun_out/r2/%s.json" % f))
+    print(f, {k: j[k] for k in j if k not in ("families", "config", "one_tile_cta_cycles")})
+    for r in j["one_tile_cta_cycles"][:8]: print(r)
+    for r in j["families"][:8]: print(r)
+PY

@@ -498,3 +498,36 @@ def test_gemm_chain(M, K1, N1, N2, act, act_dt, parity_log):
     err = (y - ref).abs().max().item()
     parity_log(test="gemm_chain", M=M, K1=K1, N1=N1, N2=N2, act=act, dtype=str(act_dt), max_abs_err=err)
     assert err < (5e-3 if f16 else 4e-2), err
+
+
+@pytest.mark.parametrize("M,N,K,act", [
+    (128, 128, 64, 0),          # one tile, one k-block
+    (256, 256, 1024, 0),        # the 2-stage ring wraps eight times
+    (200, 384, 768, 1),         # ragged M, GELU
+    (1984, 3072, 768, 1),       # text FFN-in at batch 64: 384 tiles on 3 x 148 slots
+    (2304, 3072, 1024, 0),      # image QKV: 432 tiles
+    (64, 3129, 2048, 0),        # ragged N (per-lane remainder path)
+    (15872, 768, 768, 2),       # 744 tiles: CTAs walk several tiles on ONE accumulator (tmem_empty hand-shake)
+])
+@pytest.mark.parametrize("act_dt", ACT)
+def test_linear_three_ctas_per_sm(M, N, K, act, act_dt, parity_log):
+    """PCfg MODE 6 (variant 3: three CTAs per SM, 2-stage ring, one accumulator, four software-pipelined epilogue warps): same tiles and
+    k order as the default kernel -> the same bits in the fp32 and in the 16-bit output."""
+    global VARIANT
+    x, w, b, _ = _mk(M, N, K, seed=5, act=act_dt)
+    ld = (N + 3) // 4 * 4
+    try:
+        VARIANT = 0
+        yb0, yf0 = run_linear(x, w, b, act=act, block_n=128, ld_f32=ld)
+        VARIANT = 3
+        yb3, yf3 = run_linear(x, w, b, act=act, block_n=128, ld_f32=ld)
+        yb3b, _ = run_linear(x, w, b, act=act, block_n=128, want_f32=False)           # 16-bit only: the TMA-store epilogue
+    finally:
+        VARIANT = 0
+    ref = ref_linear(x, w, b, act=act)
+    err = (yf3 - ref).abs().max().item()
+    parity_log(test="linear_three_ctas_per_sm", M=M, N=N, K=K, act=act, dtype=str(act_dt), max_abs_err=err)
+    assert err < 2e-3
+    assert torch.equal(yf0, yf3)
+    if yb0 is not None:
+        assert torch.equal(yb0, yb3) and torch.equal(yb0, yb3b)

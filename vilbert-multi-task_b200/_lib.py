@@ -66,7 +66,7 @@ class Options(C.Structure):
 
 # every symbol include/vilbert_b200.h declares (tests/test_cabi.py checks the list against the header)
 EXPORTS = ["vb200_abi_version", "vb200_create", "vb200_destroy", "vb200_last_error", "vb200_forward", "vb200_forward_slot",
-           "vb200_forward_host", "vb200_forward_host_slot", "vb200_plan_info", "vb200_model_dim", "vb200_set_option", "vb200_profile_ops",
+           "vb200_forward_host", "vb200_forward_host_slot", "vb200_plan_info", "vb200_model_dim", "vb200_set_option", "vb200_timeline", "vb200_profile_ops",
            "vb200_attention_layout", "vb200_forward_regions", "vb200_encode_text", "vb200_encode_image", "vb200_forward_cached",
            "vb200_linear", "vb200_linear_split", "vb200_linear_ln", "vb200_linear_chain", "vb200_layernorm", "vb200_layernorm_split", "vb200_attention_f32",
            "vb200_self_attention", "vb200_co_attention"]
@@ -104,6 +104,7 @@ def load():
     lib.vb200_plan_info.argtypes = [vp, i32, i32, i32, u32, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb200_model_dim.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     lib.vb200_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.vb200_timeline.argtypes = [vp, i32, i32, i32, u32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     lib.vb200_profile_ops.argtypes = [vp, i32, i32, i32, u32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(i32)]
     lib.vb200_attention_layout.argtypes = [vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]

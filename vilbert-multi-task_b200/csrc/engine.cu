@@ -391,6 +391,7 @@ struct Plan {
     struct AttnOut { float* p; int heads, Lq, Lk; };   // attention probabilities [B, heads, Lq, Lk] in schedule order
     std::vector<AttnOut> attn;                         //   (T / V layers: one entry; connection layers: text->image, image->text)
     uint64_t last_use = 0;                             // plan-cache LRU stamp
+    long long* timeline = nullptr;                     // profiling (set_option "timeline"): [GEMM op][kTimelineCtas][16] stamps of the LAST replay
     double flops = 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -423,6 +424,8 @@ struct vb200_engine {
     bool wide192 = false;      // VB200_BN192=1: 128x192 tiles for GEMMs that need more than one wave of 128-wide ones.  Faster per
                                // launch (FFN-in 18.5 -> 16.2 us, image QKV 16.9 -> 14.9 us, 973 TFLOP/s) but the STEP is 3 % slower
                                // with them (38.8 k vs 40.1 k pairs/s, profiles/r2_tile192.md) -- opt-in
+    int tri_min_tiles = 0;     // VB200_TRI=<tiles> (0 = off): plain 128-wide GEMMs with at least this many tiles run THREE CTAs per SM
+                               // (PCfg MODE 6: 2-stage ring, one accumulator, four epilogue warps)
     bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
@@ -460,6 +463,7 @@ struct vb200_engine {
     float* lm_bias = nullptr;
     std::map<std::string, HostTensor> sd;
     std::map<std::vector<int64_t>, std::unique_ptr<Plan>> plans;
+    bool timeline = false;          // vb200_set_option("timeline", 1): plans built from now on record per-CTA stamps (vb200_timeline)
     int profile_grid_pct = 0;       // vb200_set_option("profile_grid_pct"): persistent-grid override for vb200_profile_ops only
     uint64_t use_clock = 0;         // LRU clock of the plan cache
     size_t max_plans = 24;          // VB200_MAX_PLANS: least-recently-used plans beyond this are destroyed (workspace + graph)
@@ -870,6 +874,8 @@ struct vb200_engine {
         op.tb = make_tmap(W.w, W.N, static_cast<int64_t>(W.ldw) * S, static_cast<int64_t>(W.ldw) * S, op.pair ? op.block_n / 2 : op.block_n,
                           opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
+        if (tri_min_tiles > 0 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && op.block_n == 128 &&
+            ((a_rows + 127) / 128) * ((W.N + 127) / 128) >= tri_min_tiles) e.tri = 1;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw * S;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : (opt.use_pdl ? (early_w ? 5 : 1) : 0);
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
@@ -1160,6 +1166,7 @@ struct vb200_engine {
 
         link_chains(pl);
         link_pdl(pl);
+        if (timeline) attach_timeline(pl);
         // One eager pass first: opts kernels into their shared-memory sizes and surfaces launch-configuration
         // errors with a real message (errors inside a capture only invalidate the capture).
         if (!ops.empty()) {
@@ -1176,6 +1183,20 @@ struct vb200_engine {
         plans[key] = std::move(up);
         evict_plans(raw);
         return raw;
+    }
+
+    // Profiling: every plain persistent GEMM of the plan writes its per-CTA stamps (gemm_persistent.cuh: entry / exit %globaltimer, SM id,
+    // clock64 at setup done, first k-block landed, last MMA committed, epilogue done) into a plan-owned buffer; a replay overwrites the
+    // previous one, so after a run the buffer holds the LAST forward of this plan (scripts/step_timeline.py reads two slots' worth).
+    static constexpr int kTimelineCtas = 304;
+    void attach_timeline(Plan& pl) {
+        size_t n = 0;
+        for (const Op& op : pl.ops) if (op.kind == Op::GEMM && !op.pair && !op.ln && !op.chain_sync) ++n;
+        if (n == 0) return;
+        pl.timeline = pl.mem.alloc_n<long long>(n * kTimelineCtas * 16);
+        CUDA_CHECK(cudaMemset(pl.timeline, 0, n * kTimelineCtas * 16 * sizeof(long long)));
+        size_t i = 0;
+        for (Op& op : pl.ops) if (op.kind == Op::GEMM && !op.pair && !op.ln && !op.chain_sync) op.ep.timing = pl.timeline + (i++) * kTimelineCtas * 16;
     }
 
     // Plan cache bound (a MicroBatchWorker produces many (batch, length, regions) combinations): beyond max_plans the least
@@ -1614,6 +1635,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         eng->fused_ln = o.fused_layernorm != 0;
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
         if (const char* v = getenv("VB200_BN192")) eng->wide192 = (strcmp(v, "0") != 0);
+        if (const char* v = getenv("VB200_TRI")) eng->tri_min_tiles = std::max(0, atoi(v));
         if (const char* v = getenv("VB200_CHAIN")) eng->chain_ffn = (strcmp(v, "0") != 0);
         eng->ln_fold = o.ln_fold > 0;
         if (const char* v = getenv("VB200_LNFOLD")) eng->ln_fold = (strcmp(v, "0") != 0);
@@ -1842,6 +1864,12 @@ int vb200_set_option(vb200_handle h, const char* key, int64_t value) {
         } else if (k == "max_plans") {
             if (value < 1) fail(VB200_ERR_INVALID, "max_plans must be positive");
             h->max_plans = static_cast<size_t>(value);
+        } else if (k == "timeline") {
+            if ((value != 0) != h->timeline) {
+                CUDA_CHECK(cudaDeviceSynchronize());
+                h->plans.clear();
+                h->timeline = value != 0;
+            }
         } else if (k == "chain_ffn") {
             // changes how plans are built: drop the cached ones (the device is drained first, a plan may still be executing)
             if ((value != 0) != h->chain_ffn) {
@@ -1850,6 +1878,28 @@ int vb200_set_option(vb200_handle h, const char* key, int64_t value) {
                 h->chain_ffn = value != 0;
             }
         } else fail(VB200_ERR_INVALID, "unknown option \"%s\"", key);
+    });
+}
+
+int vb200_timeline(vb200_handle h, int32_t batch, int32_t n_tokens, int32_t n_regions, uint32_t select, int32_t slot, int32_t max_ops,
+                   int32_t* n_ops, int32_t* dims, int64_t* stamps) {
+    if (h == nullptr || n_ops == nullptr) return VB200_ERR_INVALID;
+    return guard(h, [&] {
+        CUDA_CHECK(cudaSetDevice(h->opt.device));
+        if (!h->timeline) fail(VB200_ERR_INVALID, "vb200_timeline: set_option(\"timeline\", 1) first");
+        Plan* pl = h->get_plan(batch, n_tokens, n_regions, select & VB200_OUT_ALL, slot);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        int n = 0;
+        for (const Op& op : pl->ops) {
+            if (op.ep.timing == nullptr || op.kind != Op::GEMM) continue;
+            if (n < max_ops) {
+                if (dims) { dims[4 * n] = op.ep.M; dims[4 * n + 1] = op.ep.N; dims[4 * n + 2] = op.ep.K; dims[4 * n + 3] = op.stream; }
+                if (stamps) CUDA_CHECK(cudaMemcpy(stamps + static_cast<size_t>(n) * vb200_engine::kTimelineCtas * 16, op.ep.timing,
+                                                  sizeof(long long) * vb200_engine::kTimelineCtas * 16, cudaMemcpyDeviceToHost));
+            }
+            ++n;
+        }
+        *n_ops = n;
     });
 }
 
@@ -1887,7 +1937,8 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
     return op_guard([&] {
         const bool ln = gamma != nullptr;
         const bool pair = variant == 2;                                    // CTA-pair kernel: block_n 128 (default) or 256
-        if (variant != 0 && variant != 2) fail(VB200_ERR_INVALID, "vb200_linear: variant %d does not exist (0 persistent, 2 CTA pair)", variant);
+        if (variant != 0 && variant != 2 && variant != 3)
+            fail(VB200_ERR_INVALID, "vb200_linear: variant %d does not exist (0 persistent, 2 CTA pair, 3 persistent with three CTAs per SM)", variant);
         int bn = block_n > 0 ? block_n : (pair ? 128 : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
         if (bn == 0) fail(VB200_ERR_INVALID, "no tiling for N=%lld with LayerNorm", (long long)N);
         CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128, act_fp16 != 0);
@@ -1900,7 +1951,11 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
         if (const char* dbg = getenv("VB200_DEBUG")) e.debug = atoi(dbg);          // timing decomposition (kernels.h), op entry only
         CUtensorMap tc;
         const char* ts = getenv("VB200_TMASTORE");
-        if (variant == 0 && !ln && !(ts && strcmp(ts, "0") == 0)) { setup_tma_store(&tc, e); e.tmap_c_host = e.tma_store ? &tc : nullptr; }
+        if (variant == 3) {
+            if (ln || bn != 128) fail(VB200_ERR_INVALID, "vb200_linear: variant 3 is the plain 128-wide tile");
+            e.tri = 1;
+        }
+        if (variant != 2 && !ln && !(ts && strcmp(ts, "0") == 0)) { setup_tma_store(&tc, e); e.tmap_c_host = e.tma_store ? &tc : nullptr; }
         if (pair) CUDA_CHECK(vb::launch_gemm_pair(ta, tb, e, bn, static_cast<cudaStream_t>(cuda_stream)));
         else CUDA_CHECK(vb::launch_gemm_persistent(ta, tb, e, bn, ln, static_cast<cudaStream_t>(cuda_stream)));
     });

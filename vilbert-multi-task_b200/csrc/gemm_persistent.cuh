@@ -46,6 +46,13 @@ template <int BLOCK_N, bool LN, bool EPI8 = LN, int MODE = 0>
 struct PCfg {
     static constexpr bool WIDE2 = MODE == 2;
     static_assert(!WIDE2 || ((BLOCK_N == 256 || BLOCK_N == 192) && !LN), "WIDE2 is the 192- / 256-wide plain tile");
+    // MODE 6 ("TRI"): THREE CTAs per SM for the GEMMs with more tiles than 2 x 148 -- 128x128 tiles, 2-stage ring (64 KB), one 128-column
+    // accumulator, four epilogue warps (192 threads x 112 registers x 3 fit the register file; 3 x 75 KB the shared memory; 3 x 128 columns
+    // TMEM).  The same six stages per SM are in flight as with 2 x 3, but three CTAs are in three different phases: while one sits in its
+    // prologue or drains its accumulator the other two feed the tensor pipe (profiles/r2_step_timeline.md: a one-tile CTA spends only half
+    // of its life in the main loop, and with two slots an SM has NO main loop running 45 % of the time).
+    static constexpr bool TRI = MODE == 6;
+    static_assert(!TRI || (BLOCK_N == 128 && !LN), "TRI is the 128-wide plain tile");
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
@@ -54,22 +61,22 @@ struct PCfg {
     // an SM needs ~6 stages in flight to be MMA-bound.  Plain tiles: 3 stages x 2 CTAs per SM (the second CTA also lets a
     // kernel of the other ViLBERT stream share the SM).  LayerNorm tiles run one CTA per SM (clusters, 8 epilogue warps
     // with the row slice in registers) and take the whole ring themselves.
-    static constexpr int kEpiWarps = (LN || EPI8) ? 8 : 4;
+    static constexpr int kEpiWarps = (LN || (EPI8 && !TRI)) ? 8 : 4;
     static constexpr int kEpiThreads = 32 * kEpiWarps;
     // warp 0 TMA, warp 1 MMA (+TMEM alloc), then the epilogue warps
     static constexpr int kThreads = 64 + kEpiThreads;
-    static constexpr int kMinBlocks = WIDE2 ? 2 : ((LN || BLOCK_N >= 192) ? 1 : 2);
+    static constexpr int kMinBlocks = TRI ? 3 : (WIDE2 ? 2 : ((LN || BLOCK_N >= 192) ? 1 : 2));
     // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
     // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
     //   plain: 32 rows x 64 bytes, XOR-swizzled (store16_sw / store_f32_sw);  LN: 32 rows x 33 fp32
     static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 2048;      // plain: 32 rows x 64 B, swizzled (store16_sw)
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
-    static constexpr int kStages = WIDE2 ? 2 : (kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit));
+    static constexpr int kStages = (WIDE2 || TRI) ? 2 : (kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit));
     // Accumulator layout in TMEM: two buffers of BLOCK_N columns (epilogue of tile i overlaps the MMAs of tile i+1); WIDE2: one.
     // (A lone CTA runs at ~536 cycles per k-block whatever BLOCK_N -- profiles/r1_mma_issue_rate.txt; the round-1 "DEEP" variant
     // with a second MMA-issuing warp was faster alone and slower in the step, and was removed in round 2.)
-    static constexpr int kAccBufs = WIDE2 ? 1 : 2;
+    static constexpr int kAccBufs = (WIDE2 || TRI) ? 1 : 2;
     static constexpr int kAccCols = kAccBufs * BLOCK_N;
     static_assert(kAccCols <= 512, "TMEM has 512 columns");
     static constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
@@ -86,7 +93,7 @@ struct PCfg {
     // no alignment slack: the dynamic shared-memory window starts 1024-aligned (checked at kernel entry).  An SM has 233472
     // bytes and every CTA costs its dynamic size + 1024 reserved.
     static constexpr int kSmemBytes = kStages * kStageBytes + kSmemAux;
-    static_assert(kMinBlocks == 1 ? kSmemBytes <= 232448 : 2 * (kSmemBytes + 1024) <= 233472, "shared memory budget");
+    static_assert(kMinBlocks == 1 ? kSmemBytes <= 232448 : kMinBlocks * (kSmemBytes + 1024) <= 233472, "shared memory budget");
 };
 
 // ---- cluster-scope mbarrier helpers (LayerNorm exchange)
@@ -152,6 +159,16 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, tied to the registers of a load that was issued EARLIER than the code just above this call (software-pipelined
+// epilogue): the "+f" operands make every later use of v depend on the wait, so nothing that reads v can be scheduled ahead of it.
+__device__ __forceinline__ void tmem_ld_wait_for(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+                   "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]),
+                   "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
+}
 
 // ---- straight-line per-chunk epilogue pieces (all flags resolved outside the element loops)
 template <int ACT>
@@ -436,6 +453,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         stamps[8] = static_cast<long long>(gt);                                    // ns, for launch-ramp analysis
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        stamps[12] = smid;                                                         // per-SM occupancy (scripts/step_timeline.py)
     }
 
     // ---- tile assignment.  Non-LN: CTA b takes tiles b, b+grid, ... with the N index fastest (CTAs that run together
@@ -510,6 +530,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             int s = 0;
             uint32_t phase = 0;
             if (p.pdl == 5 && !LN) pdl_wait();
+#ifdef VB200_STAMPS
+            if (stamps && !LN) stamps[6] = clock64();                  // producer past griddepcontrol.wait (non-LN kernels: slot 6 is free)
+#endif
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
                 const int m0 = (LN ? tile : tile / num_n_tiles) * kBlockM;
                 const int n0 = (LN ? static_cast<int>(my_rank) : tile % num_n_tiles) * BLOCK_N;
@@ -644,7 +667,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                      (p.tma_store == 1 || kF32SlabsFit) &&
                                      (p.tma_store == 1 ? (p.out_bf16 != nullptr && p.out_f32 == nullptr)
                                                        : (p.out_f32 != nullptr && p.out_bf16 == nullptr));
-                auto finish_chunk = [&](float (&v)[32], int nc) {
+                auto finish_chunk = [&](float (&v)[32], int nc) __attribute__((always_inline)) {
                     if constexpr (MODE == 4) {                       // y = rstd * (acc - mean * s) + c; c arrives as the bias below
                         const float4* s4 = reinterpret_cast<const float4*>(p.fold_s + nc);
                         const float ms = -a_mean * a_rstd;
@@ -756,7 +779,29 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         store_chunk<F16>(ps, m, nc, false, v);
                     }
                 };
-                {
+                if constexpr (Cfg::TRI) {
+                    // four warps, one per TMEM lane quarter, all kNC chunks each; software-pipelined: the load of chunk c + 1 is in
+                    // flight while chunk c is finished (two chunks in registers -- the 112-register budget of this mode allows it)
+                    static_assert(kNC % 2 == 0, "pipelined in pairs");
+                    float va[32], vb[32];
+                    tmem_ld32_issue(taddr, va);
+#pragma unroll
+                    for (int c = 0; c < kNC; c += 2) {
+                        tmem_ld_wait_for(va);
+                        tmem_ld32_issue(taddr + (c + 1) * 32, vb);
+                        if (stamp && c == 0) stamps[14] = clock64();
+                        finish_chunk(va, n0 + c * 32);
+                        if (stamp && c == 0) stamps[15] = clock64();
+                        tmem_ld_wait_for(vb);
+                        if (c + 2 < kNC) {
+                            tmem_ld32_issue(taddr + (c + 2) * 32, va);
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(&tmem_empty_bar[acc]);         // the accumulator is in registers: the next tile's MMAs may start
+                        }
+                        finish_chunk(vb, n0 + (c + 1) * 32);
+                    }
+                } else {
                     // eight warps: column group g = ew / 4 takes chunks [g * kNC/2, (g+1) * kNC/2); thread-level parallelism
                     // hides the TMEM latency, one chunk in registers at a time keeps two CTAs per SM within 102 registers
                     constexpr int kCPG = kNC / 2;
@@ -902,6 +947,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         stamps[9] = static_cast<long long>(gt);
+        stamps[13] = clock64();
     }
 }
 

@@ -74,7 +74,9 @@ cudaError_t launch_gemm_persistent_plain(const CUtensorMap& ta, const CUtensorMa
     }
     switch (block_n) {
         case 64: return dispatch_plain<64>(ta, tb, ep, st);
-        case 128: return dispatch_plain<128>(ta, tb, ep, st);
+        case 128:
+            if (ep.tri) return dispatch_act<128, 6>(ta, tb, ep, st);        // three CTAs per SM (PCfg MODE 6)
+            return dispatch_plain<128>(ta, tb, ep, st);
         case 192:                                    // 128x192 tiles, two CTAs per SM, 2-stage ring, one accumulator (PCfg MODE 2)
             if (ep.N % 192 != 0) return cudaErrorInvalidValue;
             return dispatch_act<192, 2>(ta, tb, ep, st);
