@@ -54,6 +54,8 @@ def parse():
                         "as `alt`; fp32x = fp32-parity mode (split operands, 3x the tensor work)")
     p.add_argument("--inflight", type=int, default=2,
                    help="batches in flight per GPU: steps alternate over this many CUDA streams / engine workspace slots")
+    p.add_argument("--e2e-inflight", type=int, default=0,
+                   help="workspace slots the host-buffer (e2e) loop submits into; 0 = --inflight + 1 (1 when --inflight is 1)")
     p.add_argument("--ops-table", default="", help="write the per-shape kernel time table (isolated graph replays) to this file")
     p.add_argument("--fused-ln", action="store_true", help="cluster-LayerNorm GEMM epilogue instead of GEMM + row LayerNorm")
     p.add_argument("--captions", type=int, default=1000, help="retrieval: captions (rows of the score matrix)")
@@ -277,39 +279,50 @@ def measure_vqa(args, model, reqs, dev, world, rank, local_rank, select, with_pr
     assert torch.isfinite(out[0]).all(), "non-finite logits"
     value = B * world * args.steps / (ms * 1e-3)
 
-    # ---- e2e: host-buffer C-ABI call, pinned inputs, H2D + forward + D2H of the logits inside the timed region
+    # ---- e2e: host-buffer C-ABI call, pinned inputs, H2D + forward + D2H of the logits inside the timed region.  The host submits
+    # into `--e2e-inflight` workspace slots (default 3): one more than the device-side measurement, so that the blocking wait for a
+    # slot's previous step (its pinned logits must be final before the slot is re-used) does not starve the GPU of submissions.
+    enfl = args.e2e_inflight if args.e2e_inflight > 0 else (nfl + 1 if nfl > 1 else 1)
+    if args.no_graph:
+        enfl = 1
+    estreams = streams + [torch.cuda.Stream(device=dev) for _ in range(enfl - len(streams))] if enfl > 1 else [torch.cuda.current_stream(dev)]
     hreqs = [[t.pin_memory() for i, t in enumerate(r) if i != 6] for r in reqs]
-    houts = [{"vil_prediction": torch.empty(B, 3129, dtype=torch.float32).pin_memory()} for _ in range(nfl)]
+    houts = [{"vil_prediction": torch.empty(B, 3129, dtype=torch.float32).pin_memory()} for _ in range(enfl)]
     out_bytes = houts[0]["vil_prediction"].numel() * 4
 
     def estep(i):
-        # host-buffer C-ABI call on slot/stream i % nfl: H2D of this step's inputs, forward, D2H of its logits -- all inside
+        # host-buffer C-ABI call on slot/stream i % enfl: H2D of this step's inputs, forward, D2H of its logits -- all inside
         # the timed region.  A slot is re-used only after its previous step has completed (its pinned logits are final then),
-        # so with nfl slots one batch's copies overlap another batch's kernels.
+        # so with several slots one batch's copies overlap another batch's kernels.
         q, f, s, seg, im, vm, tk = hreqs[i % args.rotate]
-        j = i % nfl
-        if nfl == 1:
+        j = i % enfl
+        if enfl == 1:
             return model.forward_host(q, f, s, seg, im, vm, tk, houts[0], select=L.OUT_VIL_PREDICTION)
-        streams[j].synchronize()
-        with torch.cuda.stream(streams[j]):
+        estreams[j].synchronize()
+        with torch.cuda.stream(estreams[j]):
             model.forward_host(q, f, s, seg, im, vm, tk, houts[j], select=L.OUT_VIL_PREDICTION, slot=j, synchronize=False)
 
-    for i in range(max(args.warmup, 3) * nfl):
+    def esync():
+        for st_ in estreams:
+            st_.synchronize()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3) * enfl):
         estep(i)
-    sync_all()
+    esync()
     t0 = time.perf_counter()
     for i in range(args.steps):
         estep(i)
-    sync_all()                         # every stream drained: the logits of all steps are in host memory
+    esync()                            # every stream drained: the logits of all steps are in host memory
     e2e_s = time.perf_counter() - t0
     e2e_s = all_rank_ms(e2e_s, world, dev)[0]
     e2e_value = B * world * args.steps / e2e_s
-    hout = houts[(args.steps - 1) % nfl]
+    hout = houts[(args.steps - 1) % enfl]
     chk = model(*dreqs[(args.steps - 1) % args.rotate], select=L.OUT_VIL_PREDICTION)[0].cpu()
     assert torch.allclose(chk, hout["vil_prediction"], atol=1e-5), "host/device C-ABI paths disagree"
 
     res = dict(value=value, ms=ms, per_rank_ms=per_rank, e2e_value=e2e_value, e2e_s=e2e_s, in_bytes=in_bytes, out_bytes=out_bytes,
-               n_launch=int(n_launch), flops=flops, nfl=nfl, clocks=sampler.result(), timed_region_s=ms * 1e-3)
+               n_launch=int(n_launch), flops=flops, nfl=nfl, enfl=enfl, clocks=sampler.result(), timed_region_s=ms * 1e-3)
     if with_profile:
         # ---- per-kernel times, live: every kernel of the step replayed from its own CUDA graph between two CUDA events
         ops = model.profile_ops(B, Tin, V, select, iters=5)
@@ -404,7 +417,7 @@ def run_vqa(args):
                        "cuda_graph": not args.no_graph, "pdl": "every kernel" if args.pdl != "off" else "off", "layernorm": "fused" if args.fused_ln else "split",
                        "heads": "task heads" if args.all_heads else "vil_prediction"},
             "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": m["out_bytes"],
-                    "ms_per_step": 1e3 * m["e2e_s"] / args.steps},
+                    "ms_per_step": 1e3 * m["e2e_s"] / args.steps, "batches_in_flight": m["enfl"]},
             "gpu_launches": m["n_launch"] * args.steps,
             "launches_per_step": m["n_launch"],
             "parity": {"max_abs_err_vs_fp32_oracle": par[0] if par else None, "logit_std": par[1] if par else None,
