@@ -149,6 +149,23 @@ def test_config_json_garbage():
     assert lib.vb200_create(b"{}", 0, None, None, C.byref(h)) == -3
 
 
+def test_config_json_string_escapes():
+    """The engine's JSON reader decodes escape sequences (RFC 8259 section 7): "g\\u0065lu" is "gelu"; a broken \\u escape and an
+    escaped value that is NOT gelu are configuration errors, not silently accepted strings."""
+    lib = L.load()
+    h = C.c_void_p()
+    t = (L.Tensor * 1)()
+    x = torch.zeros(1)
+    t[0].name, t[0].ndim, t[0].data = b"x", 1, x.data_ptr()
+    t[0].shape[0] = 1
+    ok = b'{"hidden_act": "g\\u0065lu", "v_hidden_act": "gel\\u0075", "note": "a \\"quoted\\" \\\\ path\\n"}'
+    assert lib.vb200_create(ok, 1, t, None, C.byref(h)) == -3                     # config accepted; the 1-tensor checkpoint is what fails
+    assert "x" in lib.vb200_last_error(None).decode() or "missing" in lib.vb200_last_error(None).decode()
+    assert lib.vb200_create(b'{"hidden_act": "g\\u00zzlu"}', 1, t, None, C.byref(h)) == -2
+    assert lib.vb200_create(b'{"hidden_act": "r\\u0065lu"}', 1, t, None, C.byref(h)) == -2
+    assert "gelu" in lib.vb200_last_error(None).decode()
+
+
 def test_bertconfig_protocol(tmp_path):
     """worker.py:495-522: from_json_file, attribute mutation, to_dict round trip."""
     p = tmp_path / "bert_base_6layer_6conect.json"

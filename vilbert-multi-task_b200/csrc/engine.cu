@@ -70,8 +70,32 @@ struct JsonParser {
         ++p;
         std::string s;
         while (*p && *p != '"') {
-            if (*p == '\\' && p[1]) { ++p; }
-            s.push_back(*p++);
+            if (*p != '\\') { s.push_back(*p++); continue; }
+            ++p;                                                   // escape sequence (RFC 8259 section 7)
+            switch (*p) {
+                case 'n': s.push_back('\n'); break;
+                case 't': s.push_back('\t'); break;
+                case 'r': s.push_back('\r'); break;
+                case 'b': s.push_back('\b'); break;
+                case 'f': s.push_back('\f'); break;
+                case 'u': {                                        // \uXXXX -> UTF-8 (basic multilingual plane; surrogates kept as-is)
+                    unsigned cp = 0;
+                    for (int i = 1; i <= 4; ++i) {
+                        const char c = p[i];
+                        const int d = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : -1;
+                        if (d < 0) fail(VB200_ERR_CONFIG, "config JSON: bad \\u escape");
+                        cp = cp * 16 + static_cast<unsigned>(d);
+                    }
+                    p += 4;
+                    if (cp < 0x80) s.push_back(static_cast<char>(cp));
+                    else if (cp < 0x800) { s.push_back(static_cast<char>(0xC0 | (cp >> 6))); s.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
+                    else { s.push_back(static_cast<char>(0xE0 | (cp >> 12))); s.push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F))); s.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
+                    break;
+                }
+                case '\0': fail(VB200_ERR_CONFIG, "config JSON: unterminated string");
+                default: s.push_back(*p);                          // \" \\ \/
+            }
+            ++p;
         }
         if (*p != '"') fail(VB200_ERR_CONFIG, "config JSON: unterminated string");
         ++p;

@@ -36,7 +36,7 @@ constexpr int kUmmaK = 16;
 // MODE 0: default.  MODE 3: the same kernel with the fp32-parity mode's hi | lo | hi 16-bit output (a compile-time variant so the
 // default kernel's 96-register budget is untouched).  MODE 4 / 5: the LayerNorm fold (see row_stats below) -- 4 ("FOLD") consumes an
 // activation whose LayerNorm is still pending, 5 ("LNOUT") produces one.  MODE 2 ("WIDE2", BLOCK_N = 192 or 256):
-// 128x192 is the default tile of the N = 3072 GEMMs at batch 64 (round 2): 256 / 288 tiles = ONE wave of the 296 CTA slots where
+// 128x192 (opt-in, VB200_BN192=1) gives the N = 3072 GEMMs at batch 64 256 / 288 tiles = ONE wave of the 296 CTA slots where
 // 128-wide tiles give 384 / 432 (1.3 - 1.5 waves), and a 192-wide MMA takes 96 cycles, so two co-resident issuers (~530 cycles per
 // k-block each, profiles/r2_gemm_decomposition.md) keep the tensor pipe ~90 % busy instead of ~78 %.  The 256-wide form:
 // 128x256 tiles at TWO CTAs per SM -- a 256-wide MMA takes 128 cycles, so the one-issuer limit (134 cycles per MMA) does not
