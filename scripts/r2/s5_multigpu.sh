@@ -12,6 +12,6 @@ timeout 600 $RUN bench.py --gpus $N --workload multitask --steps 100 --warmup 5 
 rm -f $O/s5_nccl_raw_n$N.*; NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT NCCL_DEBUG_FILE=$O/s5_nccl_raw_n$N.%p timeout 900 $RUN bench.py --gpus $N --workload retrieval --captions $CAP --images $IMG --steps 1 --warmup 1 --batch 256 \
     > $O/s5_retrieval_n$N.json 2> $O/s5_retrieval_n$N.err
 cat $O/s5_nccl_raw_n$N.* 2>/dev/null | grep -E "nranks|NVLS|Init COMPLETE|NCCL version" | sort | uniq -c | sort -rn | head -60 | cut -c1-260 > $O/s5_nccl_n$N.txt; rm -f $O/s5_nccl_raw_n$N.*
-timeout 600 $RUN bench.py --gpus $N --steps 100 --warmup 5 --dtype fp16 > $O/s5_vqa_n$N.json 2> $O/s5_vqa_n$N.err
+timeout 600 $RUN bench.py --gpus $N --steps 100 --warmup 5 > $O/s5_vqa_n$N.json 2> $O/s5_vqa_n$N.err
 for w in multitask retrieval vqa; do echo "== $w"; cut -c1-1500 $O/s5_${w}_n$N.json; tail -n 4 $O/s5_${w}_n$N.err | cut -c1-300; done
 wc -l $O/s5_nccl_n$N.txt; head -5 $O/s5_nccl_n$N.txt | cut -c1-200

@@ -415,3 +415,38 @@ def test_chained_ffn_launch_is_bit_identical(full_oracle, parity_log):
     eng.set_option("chain_ffn", 0)
     assert eng.plan_info(16, 30, 36, L.OUT_TASK_HEADS)[0] == n_plain
     eng.close()
+
+
+# ----------------------------------------------------------------------------------------------- step timeline (profiling hook)
+def test_timeline_records_every_gemm_cta(tiny_oracle):
+    """set_option("timeline", 1): every plain tcgen05 GEMM launch of a forward leaves per-CTA stamps (entry / exit %globaltimer, SM id);
+    the logits are the same bits as without the hook."""
+    import ctypes as C
+    import numpy as np
+    from vilbert_b200 import _lib as L
+    inp = _tiny_inputs(tiny_oracle, 4, 30, 36, 94)
+    dev = [t.cuda() for t in inp]
+    eng = _engine(tiny_oracle)
+    sel = L.OUT_VIL_PREDICTION
+    plain = eng(*dev, select=sel)[0].clone()
+    eng.set_option("timeline", 1)
+    out = eng(*dev, select=sel)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(plain, out)
+    cap, ctas = 256, 304
+    n = C.c_int32()
+    dims = (C.c_int32 * (4 * cap))()
+    st = np.zeros((cap, ctas, 16), dtype=np.int64)
+    L.check(L.load().vb200_timeline(eng._handle, 4, 30, 36, sel, 0, cap, C.byref(n), dims, st.ctypes.data_as(C.POINTER(C.c_int64))), eng._handle)
+    assert 100 <= n.value <= cap                                   # 125 GEMM launches minus whatever runs on the LN / pair variants
+    for o in range(n.value):
+        M, N, K = dims[4 * o], dims[4 * o + 1], dims[4 * o + 2]
+        live = st[o][:, 9] > 0
+        tiles = ((M + 127) // 128) * ((N + 63) // 64)                              # 64-wide tiles at most
+        assert 1 <= live.sum() <= min(tiles, 296), (o, M, N, K, int(live.sum()))
+        s = st[o][live]
+        assert (s[:, 9] >= s[:, 8]).all() and (s[:, 13] > s[:, 0]).all()          # exit after entry (globaltimer and clock64)
+        assert (s[:, 12] >= 0).all() and (s[:, 12] < 148).all()                      # SM id
+    eng.set_option("timeline", 0)
+    assert torch.equal(eng(*dev, select=sel)[0], plain)
+    eng.close()
