@@ -468,6 +468,9 @@ struct vb200_engine {
     // cluster syncs and coarser tiles cost more than the halved W traffic saves (profiles/README.md).  VB200_PAIR=0|128|256
     // forces it off / on for every plain GEMM with >= 256 rows.
     int pair_bn = -1;
+    int pair_min_waves = 0;    // automatic CTA-pair selection: at least this many waves of 256 x 256 pair tiles.  0 = measured rule
+                               // (profiles/r2_b512.md): 2 waves when the GEMM has >= 20 row panels of 256 (batch >= ~160: 512: +5.7 %,
+                               // 384: +2 %, 192: +1 %, 256: =), else 4 (batch 128 loses 4.5 % with 2).  VB200_PAIR_MIN_WAVES overrides.
     bool fused_ln = false;     // VB200_FUSED_LN=1: cluster-LayerNorm GEMM epilogue instead of GEMM(fp32) + row LayerNorm kernel
     Arena weights;
     std::string last_error;
@@ -885,7 +888,11 @@ struct vb200_engine {
         if (op.block_n == 0) fail(VB200_ERR_INVALID, "no LayerNorm-fused GEMM tiling for N=%d", W.N);
         if (!x3 && !op.ln && !keep_pending && !fold_in && a_rows >= 256) {
             if (pair_bn > 0) op.pair = W.N % pair_bn == 0;
-            else if (pair_bn < 0) op.pair = W.N % 256 == 0 && ((a_rows + 255) / 256) * (W.N / 256) >= 4 * (vb::num_sms_host() / 2);
+            else if (pair_bn < 0) {
+                const long long panels = (a_rows + 255) / 256;
+                const int waves = pair_min_waves > 0 ? pair_min_waves : (panels >= 20 ? 2 : 4);
+                op.pair = W.N % 256 == 0 && panels * (W.N / 256) >= static_cast<long long>(waves) * (vb::num_sms_host() / 2);
+            }
             if (op.pair) op.block_n = pair_bn > 0 ? pair_bn : 256;
         }
         if (wide192 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && W.N % 192 == 0 && op.block_n == 128) {
@@ -1677,6 +1684,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         }
         if (const char* v = getenv("VB200_TMASTORE")) eng->tma_store_enabled = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_EARLYW")) eng->early_w = (strcmp(v, "0") != 0);
+        if (const char* v = getenv("VB200_PAIR_MIN_WAVES")) eng->pair_min_waves = std::max(0, atoi(v));
         if (const char* v = getenv("VB200_PAIR")) { const int b = atoi(v); eng->pair_bn = (b == 128 || b == 256) ? b : (strcmp(v, "auto") == 0 ? -1 : 0); }
         CUDA_CHECK(cudaStreamCreateWithFlags(&eng->side_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
