@@ -510,23 +510,25 @@ def test_gemm_chain(M, K1, N1, N2, act, act_dt, parity_log):
     (15872, 768, 768, 2),       # 744 tiles: CTAs walk several tiles on ONE accumulator (tmem_empty hand-shake)
 ])
 @pytest.mark.parametrize("act_dt", ACT)
-def test_linear_three_ctas_per_sm(M, N, K, act, act_dt, parity_log):
-    """PCfg MODE 6 (variant 3: three CTAs per SM, 2-stage ring, one accumulator, four software-pipelined epilogue warps): same tiles and
-    k order as the default kernel -> the same bits in the fp32 and in the 16-bit output."""
+@pytest.mark.parametrize("kernel_variant", [3, 4], ids=["three_ctas_per_sm", "lone_cta_6_stages"])
+def test_linear_three_ctas_per_sm(M, N, K, act, act_dt, kernel_variant, parity_log):
+    """PCfg MODE 6 (variant 3: three CTAs per SM, 2-stage ring, one accumulator, four software-pipelined epilogue warps) and MODE 7
+    (variant 4: one CTA per SM, 6-stage ring -- the small-batch latency configuration): same tiles and k order as the default kernel
+    -> the same bits in the fp32 and in the 16-bit output."""
     global VARIANT
     x, w, b, _ = _mk(M, N, K, seed=5, act=act_dt)
     ld = (N + 3) // 4 * 4
     try:
         VARIANT = 0
         yb0, yf0 = run_linear(x, w, b, act=act, block_n=128, ld_f32=ld)
-        VARIANT = 3
+        VARIANT = kernel_variant
         yb3, yf3 = run_linear(x, w, b, act=act, block_n=128, ld_f32=ld)
         yb3b, _ = run_linear(x, w, b, act=act, block_n=128, want_f32=False)           # 16-bit only: the TMA-store epilogue
     finally:
         VARIANT = 0
     ref = ref_linear(x, w, b, act=act)
     err = (yf3 - ref).abs().max().item()
-    parity_log(test="linear_three_ctas_per_sm", M=M, N=N, K=K, act=act, dtype=str(act_dt), max_abs_err=err)
+    parity_log(test="linear_variant_%d" % kernel_variant, M=M, N=N, K=K, act=act, dtype=str(act_dt), max_abs_err=err)
     assert err < 2e-3
     assert torch.equal(yf0, yf3)
     if yb0 is not None:

@@ -450,6 +450,9 @@ struct vb200_engine {
                                // with them (38.8 k vs 40.1 k pairs/s, profiles/r2_tile192.md) -- opt-in
     int tri_min_tiles = 0;     // VB200_TRI=<tiles> (0 = off): plain 128-wide GEMMs with at least this many tiles run THREE CTAs per SM
                                // (PCfg MODE 6: 2-stage ring, one accumulator, four epilogue warps)
+    int lone_rows = 320;       // VB200_LONE_ROWS (0 = off): forwards with at most this many rows in either stream (batch <= 8 at the default
+                               // shapes) run their plain 128-wide GEMMs one CTA per SM with a 6-stage ring (PCfg MODE 7): nothing else is
+                               // there to share the SM, and a lone CTA's k loop is 1.5x faster with six stages in flight
     bool x3 = false;           // fp32-parity mode (vb200_options::split_fp32): fp16 hi/lo split operands, K' = 3K GEMMs, fp32 attention
     // Programmatic dependent launch.  Default: every kernel ("full": each kernel triggers its dependents once its main work is
     // issued; a dependent GEMM's producer puts its first weight tiles in flight before griddepcontrol.wait).  Measured with two
@@ -907,6 +910,8 @@ struct vb200_engine {
         GemmEpilogue& e = op.ep;
         if (tri_min_tiles > 0 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && op.block_n == 128 &&
             ((a_rows + 127) / 128) * ((W.N + 127) / 128) >= tri_min_tiles) e.tri = 1;
+        if (!e.tri && lone_rows > 0 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && op.block_n == 128 &&
+            std::max(pl.B * pl.T, pl.B * pl.V) <= lone_rows && ((a_rows + 127) / 128) * ((W.N + 127) / 128) <= vb::num_sms_host()) e.lone = 1;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw * S;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : (opt.use_pdl ? (early_w ? 5 : 1) : 0);
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
@@ -1667,6 +1672,7 @@ int vb200_create(const char* config_json, int64_t n_tensors, const vb200_tensor*
         if (const char* v = getenv("VB200_FUSED_LN")) eng->fused_ln = (strcmp(v, "1") == 0) && !eng->x3;
         if (const char* v = getenv("VB200_BN192")) eng->wide192 = (strcmp(v, "0") != 0);
         if (const char* v = getenv("VB200_TRI")) eng->tri_min_tiles = std::max(0, atoi(v));
+        if (const char* v = getenv("VB200_LONE_ROWS")) eng->lone_rows = std::max(0, atoi(v));
         if (const char* v = getenv("VB200_CHAIN")) eng->chain_ffn = (strcmp(v, "0") != 0);
         eng->ln_fold = o.ln_fold > 0;
         if (const char* v = getenv("VB200_LNFOLD")) eng->ln_fold = (strcmp(v, "0") != 0);
@@ -1969,8 +1975,8 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
     return op_guard([&] {
         const bool ln = gamma != nullptr;
         const bool pair = variant == 2;                                    // CTA-pair kernel: block_n 128 (default) or 256
-        if (variant != 0 && variant != 2 && variant != 3)
-            fail(VB200_ERR_INVALID, "vb200_linear: variant %d does not exist (0 persistent, 2 CTA pair, 3 persistent with three CTAs per SM)", variant);
+        if (variant != 0 && variant != 2 && variant != 3 && variant != 4)
+            fail(VB200_ERR_INVALID, "vb200_linear: variant %d does not exist (0 persistent, 2 CTA pair, 3 three CTAs per SM, 4 one CTA per SM with a 6-stage ring)", variant);
         int bn = block_n > 0 ? block_n : (pair ? 128 : vb::gemm_p_pick_block_n(static_cast<int>(N), ln));
         if (bn == 0) fail(VB200_ERR_INVALID, "no tiling for N=%lld with LayerNorm", (long long)N);
         CUtensorMap ta = make_tmap(x_bf16, M, K, ld_x, 128, act_fp16 != 0);
@@ -1983,9 +1989,9 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
         if (const char* dbg = getenv("VB200_DEBUG")) e.debug = atoi(dbg);          // timing decomposition (kernels.h), op entry only
         CUtensorMap tc;
         const char* ts = getenv("VB200_TMASTORE");
-        if (variant == 3) {
-            if (ln || bn != 128) fail(VB200_ERR_INVALID, "vb200_linear: variant 3 is the plain 128-wide tile");
-            e.tri = 1;
+        if (variant == 3 || variant == 4) {
+            if (ln || bn != 128) fail(VB200_ERR_INVALID, "vb200_linear: variants 3 and 4 are the plain 128-wide tile");
+            if (variant == 3) e.tri = 1; else e.lone = 1;
         }
         if (variant != 2 && !ln && !(ts && strcmp(ts, "0") == 0)) { setup_tma_store(&tc, e); e.tmap_c_host = e.tma_store ? &tc : nullptr; }
         if (pair) CUDA_CHECK(vb::launch_gemm_pair(ta, tb, e, bn, static_cast<cudaStream_t>(cuda_stream)));

@@ -53,6 +53,12 @@ struct PCfg {
     // of its life in the main loop, and with two slots an SM has NO main loop running 45 % of the time).
     static constexpr bool TRI = MODE == 6;
     static_assert(!TRI || (BLOCK_N == 128 && !LN), "TRI is the 128-wide plain tile");
+    // MODE 7 ("LONE"): ONE CTA per SM with a 6-stage ring (192 KB) -- for the small-batch forwards (batch <= ~8) whose GEMMs have far
+    // fewer tiles than the GPU has SMs, so that no second CTA is there to supply the other three stages the tensor pipe needs: a lone
+    // CTA runs 613 cycles per k-block with 3 stages and 389 with 6 (profiles/r1_mma_issue_rate.txt section 6); the launch chain of a
+    // batch-1 forward is 213 such kernels.  Never used when other kernels could share the SM (batch 64: the step got slower, ibid. 5).
+    static constexpr bool LONE = MODE == 7;
+    static_assert(!LONE || (BLOCK_N == 128 && !LN), "LONE is the 128-wide plain tile");
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
@@ -65,14 +71,14 @@ struct PCfg {
     static constexpr int kEpiThreads = 32 * kEpiWarps;
     // warp 0 TMA, warp 1 MMA (+TMEM alloc), then the epilogue warps
     static constexpr int kThreads = 64 + kEpiThreads;
-    static constexpr int kMinBlocks = TRI ? 3 : (WIDE2 ? 2 : ((LN || BLOCK_N >= 192) ? 1 : 2));
+    static constexpr int kMinBlocks = TRI ? 3 : (WIDE2 ? 2 : ((LN || LONE || BLOCK_N >= 192) ? 1 : 2));
     // Per-epilogue-warp transpose buffer so global stores are row-contiguous (a TMEM row lives in ONE lane; writing 16 B per
     // lane to 32 different rows costs 32 transactions per instruction -- measured ~370 cycles per store instruction).
     //   plain: 32 rows x 64 bytes, XOR-swizzled (store16_sw / store_f32_sw);  LN: 32 rows x 33 fp32
     static constexpr int kXposeBytesPerWarp = LN ? 32 * 33 * 4 : 2048;      // plain: 32 rows x 64 B, swizzled (store16_sw)
     static constexpr int kXposeBytes = kEpiWarps * kXposeBytesPerWarp;
     static constexpr int kFit = (200 * 1024 - kXposeBytes) / kStageBytes;
-    static constexpr int kStages = (WIDE2 || TRI) ? 2 : (kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit));
+    static constexpr int kStages = (WIDE2 || TRI) ? 2 : (LONE ? 6 : (kMinBlocks == 2 ? 3 : (kFit > 8 ? 8 : kFit)));
     // Accumulator layout in TMEM: two buffers of BLOCK_N columns (epilogue of tile i overlaps the MMAs of tile i+1); WIDE2: one.
     // (A lone CTA runs at ~536 cycles per k-block whatever BLOCK_N -- profiles/r1_mma_issue_rate.txt; the round-1 "DEEP" variant
     // with a second MMA-issuing warp was faster alone and slower in the step, and was removed in round 2.)

@@ -76,6 +76,7 @@ cudaError_t launch_gemm_persistent_plain(const CUtensorMap& ta, const CUtensorMa
         case 64: return dispatch_plain<64>(ta, tb, ep, st);
         case 128:
             if (ep.tri) return dispatch_act<128, 6>(ta, tb, ep, st);        // three CTAs per SM (PCfg MODE 6)
+            if (ep.lone) return dispatch_act<128, 7>(ta, tb, ep, st);       // one CTA per SM, 6-stage ring (PCfg MODE 7)
             return dispatch_plain<128>(ta, tb, ep, st);
         case 192:                                    // 128x192 tiles, two CTAs per SM, 2-stage ring, one accumulator (PCfg MODE 2)
             if (ep.N % 192 != 0) return cudaErrorInvalidValue;

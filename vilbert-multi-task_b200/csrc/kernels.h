@@ -48,6 +48,7 @@ struct GemmEpilogue {
     int grid_pct;                 // 0: default persistent grid (2/3 of the CTA slots, launch_p); 10..100: this percentage of them
     int ln_mode;                  // 0 none, 4 fold-in (consumer), 5 pre-LayerNorm output + statistics (producer)
     int tri;                      // plain 128-wide tile only: three CTAs per SM (gemm_persistent.cuh PCfg MODE 6)
+    int lone;                     // plain 128-wide tile only: one CTA per SM, 6-stage ring (PCfg MODE 7; small-batch latency)
     int debug;                    // timing decomposition only (VB200_DEBUG through vb200_linear): 1 = issue no MMA, 2 = no epilogue
                                   // stores, 4 = no operand loads (the ring is "filled" by plain arrives); results are garbage
 };                                //   every GEMM starts on HBM misses (weights never survive in the 126 MB L2 until the next step)
