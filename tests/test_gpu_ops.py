@@ -533,3 +533,26 @@ def test_linear_three_ctas_per_sm(M, N, K, act, act_dt, kernel_variant, parity_l
     assert torch.equal(yf0, yf3)
     if yb0 is not None:
         assert torch.equal(yb0, yb3) and torch.equal(yb0, yb3b)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(31, 768, 768, 0), (36, 3072, 1024, 1), (248, 768, 3072, 0), (288, 1024, 1024, 2), (64, 3129, 2048, 0)])
+@pytest.mark.parametrize("act_dt", ACT)
+def test_linear_lone_cta_64_wide(M, N, K, act, act_dt, parity_log):
+    """What a small forward (batch <= 8) runs: PCfg MODE 7 with 64-wide tiles (variant 4, block_n 64).  Neither the ring depth nor the
+    tile width changes an element's accumulation order: the same bits as the default 128-wide kernel."""
+    global VARIANT
+    x, w, b, _ = _mk(M, N, K, seed=6, act=act_dt)
+    ld = (N + 3) // 4 * 4
+    try:
+        VARIANT = 0
+        yb0, yf0 = run_linear(x, w, b, act=act, block_n=128, ld_f32=ld)
+        VARIANT = 4
+        yb4, yf4 = run_linear(x, w, b, act=act, block_n=64, ld_f32=ld)
+    finally:
+        VARIANT = 0
+    err = (yf4 - ref_linear(x, w, b, act=act)).abs().max().item()
+    parity_log(test="linear_lone_cta_64_wide", M=M, N=N, K=K, act=act, dtype=str(act_dt), max_abs_err=err)
+    assert err < 2e-3
+    assert torch.equal(yf0, yf4)
+    if yb0 is not None:
+        assert torch.equal(yb0, yb4)

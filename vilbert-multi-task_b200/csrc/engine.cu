@@ -904,14 +904,25 @@ struct vb200_engine {
             const long long slots = 2LL * vb::num_sms_host(), mt = (a_rows + 127) / 128;
             if (mt * ((W.N + 127) / 128) > slots && mt * (W.N / 192) <= slots) op.block_n = 192;
         }
+        // Small forwards (<= lone_rows rows in either stream, batch <= 8): one CTA per SM with a 6-stage ring (PCfg MODE 7), and 64-wide
+        // tiles while they still fit one per SM -- twice the CTAs, half the epilogue each (batch 1: 0.932 -> 0.869 ms per forward,
+        // profiles/r2_small_batch_latency.md).  Neither changes an element's accumulation order.
+        bool lone = false;
+        if (lone_rows > 0 && tri_min_tiles == 0 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && (op.block_n == 128 || op.block_n == 64) &&
+            std::max(pl.B * pl.T, pl.B * pl.V) <= lone_rows) {
+            const long long mt = (a_rows + 127) / 128;
+            if (mt * ((W.N + 127) / 128) <= vb::num_sms_host()) {
+                lone = true;
+                if (W.N % 64 == 0 && mt * (W.N / 64) <= vb::num_sms_host()) op.block_n = 64;
+            }
+        }
         op.ta = make_tmap(A, a_rows, static_cast<int64_t>(W.ldw) * S, lda * S, 128, opt.act_fp16 != 0);
         op.tb = make_tmap(W.w, W.N, static_cast<int64_t>(W.ldw) * S, static_cast<int64_t>(W.ldw) * S, op.pair ? op.block_n / 2 : op.block_n,
                           opt.act_fp16 != 0);
         GemmEpilogue& e = op.ep;
         if (tri_min_tiles > 0 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && op.block_n == 128 &&
             ((a_rows + 127) / 128) * ((W.N + 127) / 128) >= tri_min_tiles) e.tri = 1;
-        if (!e.tri && lone_rows > 0 && !x3 && !op.ln && !op.pair && !keep_pending && !fold_in && op.block_n == 128 &&
-            std::max(pl.B * pl.T, pl.B * pl.V) <= lone_rows && ((a_rows + 127) / 128) * ((W.N + 127) / 128) <= vb::num_sms_host()) e.lone = 1;
+        if (lone) e.lone = 1;
         e.M = static_cast<int>(a_rows); e.N = W.N; e.K = W.ldw * S;
         e.bias = W.bias; e.mul = mul; e.ld_mul = ld_mul; e.eps = cfg.ln_eps; e.act = act; e.pdl = pdl_light ? 2 : (opt.use_pdl ? (early_w ? 5 : 1) : 0);
         e.a_f16 = opt.act_fp16; e.out_f16 = opt.act_fp16;
@@ -1990,7 +2001,7 @@ int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t l
         CUtensorMap tc;
         const char* ts = getenv("VB200_TMASTORE");
         if (variant == 3 || variant == 4) {
-            if (ln || bn != 128) fail(VB200_ERR_INVALID, "vb200_linear: variants 3 and 4 are the plain 128-wide tile");
+            if (ln || (bn != 128 && !(variant == 4 && bn == 64))) fail(VB200_ERR_INVALID, "vb200_linear: variant 3 is the plain 128-wide tile, variant 4 the 128- or 64-wide one");
             if (variant == 3) e.tri = 1; else e.lone = 1;
         }
         if (variant != 2 && !ln && !(ts && strcmp(ts, "0") == 0)) { setup_tma_store(&tc, e); e.tmap_c_host = e.tma_store ? &tc : nullptr; }

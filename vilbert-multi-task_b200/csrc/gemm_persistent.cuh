@@ -58,7 +58,7 @@ struct PCfg {
     // CTA runs 613 cycles per k-block with 3 stages and 389 with 6 (profiles/r1_mma_issue_rate.txt section 6); the launch chain of a
     // batch-1 forward is 213 such kernels.  Never used when other kernels could share the SM (batch 64: the step got slower, ibid. 5).
     static constexpr bool LONE = MODE == 7;
-    static_assert(!LONE || (BLOCK_N == 128 && !LN), "LONE is the 128-wide plain tile");
+    static_assert(!LONE || ((BLOCK_N == 128 || BLOCK_N == 64) && !LN), "LONE is the 128- or 64-wide plain tile");
     static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
     static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;

@@ -73,7 +73,9 @@ cudaError_t launch_gemm_persistent_plain(const CUtensorMap& ta, const CUtensorMa
         return dispatch_fold<128>(ta, tb, ep, st);
     }
     switch (block_n) {
-        case 64: return dispatch_plain<64>(ta, tb, ep, st);
+        case 64:
+            if (ep.lone) return dispatch_act<64, 7>(ta, tb, ep, st);
+            return dispatch_plain<64>(ta, tb, ep, st);
         case 128:
             if (ep.tri) return dispatch_act<128, 6>(ta, tb, ep, st);        // three CTAs per SM (PCfg MODE 6)
             if (ep.lone) return dispatch_act<128, 7>(ta, tb, ep, st);       // one CTA per SM, 6-stage ring (PCfg MODE 7)
