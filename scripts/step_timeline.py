@@ -66,6 +66,7 @@ def main():
             recs.append((slot, o, tuple(dims[4 * o:4 * o + 4]), st[o]))
 
     # ---- intervals in ns (globaltimer); clock64 differences scaled by the CTA's own (exit - entry) ratio
+    iv_owner = []
     iv = []                                                 # slot, dims, sm, t_in, t_first, t_mma_end, t_out
     for slot, o, d, st in recs:
         live = st[:, 9] > 0
@@ -77,6 +78,7 @@ def main():
             first = t_in + (s[2] - s[0]) * ns_per_cyc if s[2] > 0 else t_in
             mma_end = t_in + (s[10] - s[0]) * ns_per_cyc if s[10] > 0 else t_out
             iv.append((slot, d, int(s[12]), t_in, first, mma_end, t_out, int(s[11])))
+            iv_owner.append((slot, o))
     if not iv:
         raise SystemExit("no stamps: was the library built with -DVB200_STAMPS and the timeline option set?")
     per_slot = {}
@@ -131,6 +133,31 @@ def main():
              "other_chunks_and_tma_store", "teardown"]
     out["one_tile_cta_cycles"] = [dict(M=k[0], N=k[1], K=k[2], ctas=v[0], **{n: round(v[1 + i] / v[0]) for i, n in enumerate(names)})
                                   for k, v in sorted(br.items(), key=lambda kv: -kv[1][0])]
+    # how many distinct GEMM launches (slot, op) have a CTA resident / in their main loop at a time, GPU-wide (time-weighted histogram)
+    def launches_active(key_lo, key_hi):
+        ev = []
+        # one interval per (slot, op): from its first CTA's key_lo to its last CTA's key_hi
+        agg = {}
+        for r, (slot, o) in zip(iv, iv_owner):
+            a = agg.setdefault((slot, o), [np.inf, -np.inf])
+            a[0] = min(a[0], r[key_lo]); a[1] = max(a[1], r[key_hi])
+        for lo, hi in agg.values():
+            lo, hi = max(lo, w0), min(hi, w1)
+            if hi > lo: ev += [(lo, 1), (hi, -1)]
+        ev.sort()
+        hist = np.zeros(8)
+        t, k = w0, 0
+        for tt, dlt in ev:
+            hist[min(k, 7)] += tt - t
+            t, k = tt, k + dlt
+        hist[min(k, 7)] += w1 - t
+        return (hist / (w1 - w0)).round(4).tolist()
+
+    out["gemm_launches_resident_hist"] = launches_active(3, 6)      # index = number of GEMM launches with a resident CTA (7 = 7 or more)
+    out["gemm_launches_in_main_loop_hist"] = launches_active(4, 5)
+    # CTAs resident GPU-wide (of 296 slots), time-weighted mean and the share of them that are still waiting for their producer kernel
+    res_ns = sum(min(r[6], w1) - max(r[3], w0) for r in iv if min(r[6], w1) > max(r[3], w0))
+    out["mean_gemm_ctas_resident"] = round(res_ns / (w1 - w0), 1)
     tot = sum(r[6] - r[3] for r in iv if r[3] >= w0 and r[6] <= w1)
     out["gemm_cta_ns_in_window"] = tot
     out["slot_capacity_ns"] = 296 * (w1 - w0)
