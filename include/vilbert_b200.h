@@ -252,8 +252,10 @@ int vb200_forward_cached(vb200_handle h, int32_t batch, int32_t n_tokens, int32_
 /* y = epilogue(x[M,K] (16-bit) . w[N,K]^T (16-bit)); act: 0 none, 1 GELU(erf), 2 ReLU; LayerNorm applied when gamma != NULL.
  * act_fp16 != 0: x, w and the 16-bit output y are fp16, else bf16 (parameter names keep the historical _bf16 suffix).
  * act 3 = GELU with the 1.5e-7 erf (fp32-parity mode).  variant 0: persistent kernel (gemm_persistent.cuh, what the engine
- * uses); 2: CTA-pair kernel (gemm_pair.cu, cta_group::2).
- * timing: NULL, or a device buffer of 8 int64 per CTA that receives clock64() phase stamps (profiling aid, variant 0). */
+ * uses); 2: CTA-pair kernel (gemm_pair.cu, cta_group::2); 3: persistent kernel with three CTAs per SM (128-wide tile, PCfg MODE 6);
+ * 4: persistent kernel with one CTA per SM and a 6-stage ring (128- or 64-wide tile, PCfg MODE 7 -- what the engine uses for forwards
+ * of <= 320 rows).  Variants 0, 3 and 4 produce the same bits.
+ * timing: NULL, or a device buffer of 16 int64 per CTA that receives clock64() / %globaltimer stamps (profiling aid, variants 0, 3, 4). */
 int vb200_linear(const void* x_bf16, int64_t ld_x, const void* w_bf16, int64_t ld_w, const float* bias,
                  const float* residual, int64_t ld_res, const float* gamma, const float* beta, float eps, int32_t act,
                  void* y_bf16, int64_t ld_y_bf16, float* y_f32, int64_t ld_y_f32, int64_t M, int64_t N, int64_t K,
